@@ -1,0 +1,384 @@
+"""ArteryNetwork -- the reference's network driver
+(arteryfe/artery_network.py:14-946) as a facade over one device handle.
+
+Construction does the reference's host set-up (tree geometry, nondimensional
+parameters, inlet table, topology lists, initial flow split) and uploads it
+once.  ``solve()`` then runs the whole time loop device-resident through
+``af_net_step``; the fine-grained methods (``flux``, ``problem_function``,
+``newton``, ``windkessel`` ...) keep the reference's signatures and evaluate the
+same device code the time loop uses, one call at a time.
+"""
+import configparser
+import os
+
+import numpy as np
+
+from .. import _ffi
+from ..engine import DeviceNetwork
+from .artery import Artery
+from .utils import nondimensionalise_parameters, read_inlet, _SeriesFile
+
+HEAD_WK_SCALE = (0.3, 0.01)          # artery_network.py:408-409
+
+
+class _JunctionX(np.ndarray):
+    """``an.x``: host copy of the junction unknowns that writes item
+    assignments through to the device (the reference mutates ``self.x[i]``)."""
+
+    def __new__(cls, values, dev):
+        obj = np.asarray(values, dtype=float).view(cls)
+        obj._dev = dev
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._dev = getattr(obj, '_dev', None)
+
+    def __setitem__(self, key, value):
+        np.ndarray.__setitem__(self, key, value)
+        if self._dev is not None and self.ndim == 2:
+            self._dev.set_junction_x(np.asarray(self)[None])
+
+
+class ArteryNetwork(object):
+
+    def __init__(self, param, wk_scale=None, device=0):
+        """artery_network.py:56-130.  ``param`` is a ParamParser (or anything
+        with ``.param``, ``.geo``, ``.solution`` dicts).  ``wk_scale`` overrides
+        the two hard-coded Windkessel factors of HEAD (0.3, 0.01); it can also
+        be given as ``R1_factor`` / ``R2_factor`` in the [Solution] section."""
+        order = param.param['order']
+        self.N = 2 ** order - 1
+        self.device = device
+
+        if 'alpha' in param.param.keys():
+            if 'R_term' not in param.param:
+                raise KeyError("R_term: a geometry built from 'alpha' needs a terminal radius "
+                               "(artery_network.py:66)")
+            Ru, Rd, L = self.build_geometry(order, param.param['Ru'], param.param['Rd'],
+                                            param.param['alpha'], param.param['L'], param.param['R_term'])
+            param.param['Ru'], param.param['Rd'], param.param['L'] = Ru, Rd, L
+
+        n_leaf_max = 2 ** (order - 1)
+        for key in ('R1', 'R2', 'CT'):      # scalar in the shipped demo cfg => same value on every leaf
+            if np.ndim(param.param[key]) == 0:
+                param.param[key] = np.full(n_leaf_max, float(param.param[key]))
+
+        self.nondim = nondimensionalise_parameters(param)
+        self.geo = param.geo
+        self.sol = param.solution
+        if wk_scale is None:
+            wk_scale = (self.sol.get('R1_factor', HEAD_WK_SCALE[0]), self.sol.get('R2_factor', HEAD_WK_SCALE[1]))
+        self.wk_scale = tuple(wk_scale)
+
+        rc, qc = self.nondim['rc'], self.nondim['qc']
+        Nt = self.geo['Nt']
+        self.T, self.q_ins = read_inlet(self.sol['inlet_flow_location'], Nt)
+        self.T = self.T * qc / rc ** 3
+        self.q_ins = self.q_ins / qc
+        self.dt = self.T / Nt
+
+        self.check_geometry()
+
+        self.arteries = [None] * self.N
+        for i in range(self.N):
+            if self.nondim['Ru'][i] != 0:
+                self.arteries[i] = Artery(i, self.T, self.nondim)
+        self.arteries[0].root = True
+
+        self.range_parent_arteries = [0]
+        self.range_daughter_arteries = []
+        self.range_leaf_arteries = []
+        for i in range(1, self.N):
+            if self.arteries[i] is None:
+                continue
+            self.range_daughter_arteries.append(i)
+            d1, d2 = self.daughter_arteries(i)
+            if d1 is None and d2 is None:
+                self.arteries[i].leaf = True
+                self.range_leaf_arteries.append(i)
+            else:
+                self.range_parent_arteries.append(i)
+
+        for j, i in enumerate(self.range_leaf_arteries):
+            for key in ('R1', 'R2', 'CT'):
+                self.arteries[i].param[key] = self.nondim[key][j]
+
+        self._dev = None
+        self.define_geometry()
+        self.define_solution()
+
+    # ---- topology (artery_network.py:133-192) -----------------------------------
+    def daughter_arteries(self, i):
+        out = []
+        for k in (2 * i + 1, 2 * i + 2):
+            out.append(k if k <= self.N - 1 and self.arteries[k] is not None else None)
+        return out[0], out[1]
+
+    def parent_artery(self, i):
+        return (i - 1) // 2
+
+    def sister_artery(self, i):
+        return i + 1 if i % 2 else i - 1
+
+    def build_geometry(self, order, Ru, Rd, alpha, L, R_term):
+        """artery_network.py:195-217: radii shrink by ``alpha`` per generation
+        (times the per-vessel multiplier in Ru/Rd), last-generation Rd is
+        R_term, lengths are L*Ru, second daughters are 0.01 shorter."""
+        Ru = np.array(Ru, dtype=float)
+        Rd = np.array(Rd, dtype=float)
+        lengths = np.zeros(self.N)
+        lengths[0] = L * Ru[0]
+        lo = hi = 0
+        for level in range(order):
+            last_generation = not (2 ** (level + 1) - 1 < len(Rd))
+            for p in range(lo, hi):
+                d1, d2 = 2 * p + 1, 2 * p + 2
+                Ru[d1] = alpha * Ru[p] * Ru[d1]
+                Ru[d2] = max(0, alpha * Ru[p]) * Ru[d2]
+                if last_generation:
+                    Rd[d1] = Rd[d2] = R_term
+                else:
+                    Rd[d1] = alpha * Rd[p] * Rd[d1]
+                    Rd[d2] = max(0, alpha * Rd[p]) * Rd[d2]
+                lengths[d1] = L * Ru[d1]
+                lengths[d2] = L * Ru[d2] - 0.01
+            lo += int(2 ** (level - 1))
+            hi += int(2 ** level)
+        return Ru, Rd, lengths
+
+    def check_geometry(self):
+        """artery_network.py:220-241."""
+        order = self.nondim['order']
+        for key in ('Ru', 'Rd', 'L'):
+            got = len(self.nondim[key])
+            assert got == self.N, \
+                "A network of order {} requires {} values for {}, {} were provided".format(order, self.N, key, got)
+        n1, n2, nc = (len(np.atleast_1d(self.nondim[k])) for k in ('R1', 'R2', 'CT'))
+        assert n1 == n2, "R2 must have the same number of values as R1. {} != {}".format(n2, n1)
+        assert n1 == nc, "CT must have the same number of values as R1. {} != {}".format(nc, n1)
+
+    # ---- set-up -------------------------------------------------------------------
+    def define_geometry(self):
+        """artery_network.py:244-255."""
+        for artery in self.arteries:
+            if artery is not None:
+                artery.define_geometry(self.geo)
+
+    def define_solution(self):
+        """artery_network.py:258-279: initial flows (root q_ins[0]; daughters
+        split by inlet rest areas), then the device-resident state."""
+        theta = self.sol['theta']
+        existing = [a for a in self.arteries if a is not None]
+        self._compact = {a.i: k for k, a in enumerate(existing)}
+        q0 = {0: self.q_ins[0]}
+        for i in self.range_daughter_arteries:
+            a, s = self.arteries[i], self.arteries[self.sister_artery(i)]
+            q0[i] = a.A0(0) / (a.A0(0) + s.A0(0)) * q0[self.parent_artery(i)]
+        junctions = []
+        for ip in self.range_parent_arteries:
+            i1, i2 = self.daughter_arteries(ip)
+            if i1 is None or i2 is None:
+                raise ValueError("artery %d has exactly one daughter; a parent needs two "
+                                 "(artery_network.py:111-118)" % ip)
+            junctions.append([self._compact[ip], self._compact[i1], self._compact[i2]])
+        leaves = [self._compact[i] for i in self.range_leaf_arteries]
+        nd = self.nondim
+        if self._dev is not None:
+            self._dev.close()
+        self._dev = DeviceNetwork(
+            self.geo['Nx'], self.geo['Nt'], theta, self.dt, junctions, leaves,
+            k1=nd['k1'], k2=nd['k2'], k3=nd['k3'], rho=nd['rho'], Re=nd['Re'], db=existing[0].db, p0=nd['p0'],
+            Ru=[[a._Ru for a in existing]], Rd=[[a._Rd for a in existing]], L=[[a._L for a in existing]],
+            q0=[[q0[a.i] for a in existing]],
+            R1=[[self.arteries[i].param['R1'] * self.wk_scale[0] for i in self.range_leaf_arteries]],
+            R2=[[self.arteries[i].param['R2'] * self.wk_scale[1] for i in self.range_leaf_arteries]],
+            CT=[[self.arteries[i].param['CT'] for i in self.range_leaf_arteries]],
+            q_ins=self.q_ins, device=self.device)
+        for a in existing:
+            a._attach(self._dev, self._compact[a.i])
+            a.define_solution(q0[a.i], theta)
+        self.x = np.ones([len(self.range_parent_arteries), 18])
+
+    @property
+    def x(self):
+        return _JunctionX(self._dev.get_junction_x()[0], self._dev)
+
+    @x.setter
+    def x(self, value):
+        self._dev.set_junction_x(np.asarray(value, dtype=float)[None])
+
+    def _junction_of(self, p):
+        return self.range_parent_arteries.index(p.i)
+
+    def _leaf_of(self, a):
+        return self.range_leaf_arteries.index(a.i)
+
+    # ---- boundary physics, evaluated by the device code ---------------------------
+    def flux(self, a, U, x):
+        """artery_network.py:282-300."""
+        return self._dev.eval_flux_source(a._k, [x], [U])[0, :2].copy()
+
+    def source(self, a, U, x):
+        """artery_network.py:303-326."""
+        return np.array([0.0, self._dev.eval_flux_source(a._k, [x], [U])[0, 2]])
+
+    def compute_U_half(self, a, x0, x1, U0, U1):
+        """artery_network.py:329-358."""
+        return self._dev.eval_u_half(a._k, x0, x1, U0, U1)
+
+    def windkessel(self, a, k_max=100, tol=1.0e-12):
+        """artery_network.py:361-422: outlet area of a leaf at t_(n+1); also
+        leaves the CFL-scaled ``a.dex`` behind, as the reference does."""
+        A_out, dex, its = self._dev.windkessel(self._leaf_of(a), k_max, tol)
+        a.dex = dex
+        self.last_picard_its = its
+        return A_out
+
+    compute_A_out = windkessel         # name used before HEAD (BASELINE.json, reference tests)
+
+    def structured_tree(self, a):
+        """artery_network.py:425-431 is an empty stub in the reference."""
+        raise NotImplementedError("structured_tree is not implemented by the reference either")
+
+    def initial_x(self, p, d1, d2):
+        """artery_network.py:434-461."""
+        x = np.zeros(18)
+        ends = ((p, p.param['L']), (d1, 0), (d2, 0))
+        for v, (a, xe) in enumerate(ends):
+            x[3 * v:3 * v + 3] = a.q0
+            x[9 + 3 * v:12 + 3 * v] = a.A0(xe)
+        return x
+
+    def define_x(self):
+        """artery_network.py:464-473."""
+        x = np.zeros((len(self.range_parent_arteries), 18))
+        for k, ip in enumerate(self.range_parent_arteries):
+            i1, i2 = self.daughter_arteries(ip)
+            x[k] = self.initial_x(self.arteries[ip], self.arteries[i1], self.arteries[i2])
+        self.x = x
+
+    def problem_function(self, p, d1, d2, x):
+        """artery_network.py:476-562."""
+        return self._dev.junction_eval(self._junction_of(p), [p.dex, d1.dex, d2.dex], x)[0]
+
+    def jacobian(self, p, d1, d2, x):
+        """artery_network.py:565-665."""
+        return self._dev.junction_eval(self._junction_of(p), [p.dex, d1.dex, d2.dex], x)[1]
+
+    def newton(self, p, d1, d2, x=None, k_max=30, tol=1.e-10):
+        """artery_network.py:668-710.  ``x`` is updated in place and returned."""
+        if x is None:
+            x = np.ones(18)
+        sol, solves = self._dev.junction_newton(self._junction_of(p), [p.dex, d1.dex, d2.dex], x, k_max, tol)
+        self.last_junction_solves = solves
+        np.asarray(x)[...] = sol
+        return x
+
+    def adjust_bifurcation_step(self, p, d1, d2, margin=0.05):
+        """artery_network.py:713-737."""
+        dex = self._dev.junction_cfl_dex(self._junction_of(p)) * (1 + margin) / 1.05
+        allx = self._dev.get_dex()
+        for a in (p, d1, d2):
+            allx[0, a._k] = dex
+        self._dev.set_dex(allx)
+
+    def set_inner_bc(self, ip, i1, i2):
+        """artery_network.py:740-764."""
+        p, d1, d2 = self.arteries[ip], self.arteries[i1], self.arteries[i2]
+        self.adjust_bifurcation_step(p, d1, d2)
+        k = self.range_parent_arteries.index(ip)
+        x = self.x
+        x[k] = self.newton(p, d1, d2, np.array(x[k]))
+        p.U_out = [x[k, 9], x[k, 0]]
+        d1.U_in = [x[k, 12], x[k, 3]]
+        d2.U_in = [x[k, 15], x[k, 6]]
+
+    def set_bcs(self, q_in):
+        """artery_network.py:767-786: inlet value, then every junction and
+        every leaf in ONE device launch (they only read Un)."""
+        self.arteries[0].q_in = q_in
+        self._dev.phase_boundary()
+
+    # ---- output ---------------------------------------------------------------------
+    def dump_metadata(self):
+        """artery_network.py:789-854: mesh files + data.cfg.  Meshes are written
+        as .npy vertex arrays (no HDF5 library in this environment)."""
+        out = self.sol['output_location']
+        os.makedirs(out, exist_ok=True)
+        mesh_locations = []
+        for a in self.arteries:
+            if a is not None:
+                loc = out + '/mesh_%i.npy' % a.i
+                np.save(loc, a.dx * np.arange(a.Nx + 1))
+                mesh_locations.append(loc)
+        names, locations = ['flow'], [out + '/flow']
+        if self.sol['store_area']:
+            names.append('area'); locations.append(out + '/area')
+        if self.sol['store_pressure']:
+            names.append('pressure'); locations.append(out + '/pressure')
+        N_cycles, N_cycles_store = self.geo['N_cycles'], self.sol['N_cycles_store']
+        cfg = configparser.RawConfigParser()
+        cfg.add_section('data')
+        for key, value in (
+                ('order', self.nondim['order']), ('Nx', self.geo['Nx']),
+                ('Nt', self.sol['Nt_store'] * N_cycles_store), ('T0', self.T * (N_cycles - N_cycles_store)),
+                ('T', self.T * N_cycles), ('L', str(self.nondim['L'])[1:-1]), ('rc', self.nondim['rc']),
+                ('qc', self.nondim['qc']), ('rho', self.nondim['rho']),
+                ('mesh_locations', ','.join(mesh_locations)), ('names', ','.join(names)),
+                ('locations', ','.join(locations))):
+            cfg.set('data', key, str(value))
+        with open(out + '/data.cfg', 'w') as fh:
+            cfg.write(fh)
+
+    def store_mask(self):
+        """The dump test ``n % (Nt/Nt_store) == 0`` of artery_network.py:926,
+        float modulo included, for every n of a cycle."""
+        Nt, Nt_store = self.geo['Nt'], self.sol['Nt_store']
+        return np.array([n % (Nt / Nt_store) == 0 for n in range(Nt)], dtype=np.uint8)
+
+    def solve(self, write_output=True):
+        """artery_network.py:857-946.  The whole loop runs on the device; the
+        host only enqueues it, then fetches the stored snapshots and writes
+        them in the reference's directory layout.  Returns the snapshots as a
+        dict (``t``, ``flow``, ``area``, ``pressure``: [snapshot, artery, vertex])."""
+        self.define_x()
+        if write_output:
+            self.dump_metadata()
+        Nt, N_cycles = self.geo['Nt'], self.geo['N_cycles']
+        N_cycles_store = self.sol['N_cycles_store']
+        mask = self.store_mask()
+        fields = _ffi.AF_STORE_FLOW
+        if self.sol['store_area']:
+            fields |= _ffi.AF_STORE_AREA
+        if self.sol['store_pressure']:
+            fields |= _ffi.AF_STORE_PRESSURE
+        first_cycle = N_cycles - N_cycles_store
+        self._dev.set_store(mask, first_cycle, max(1, int(mask.sum()) * N_cycles_store), fields)
+        self._dev.step(0, N_cycles * Nt)
+        self._dev.sync()
+        flags = int(self._dev.get_flags()[0])
+        if flags & _ffi.AF_FLAG_ARTERY_NOCONV:
+            raise RuntimeError("Newton solver did not converge in an artery solve "
+                               "(flags=0x%x; DOLFIN raises here, artery.py:244)" % flags)
+        snaps = self._dev.fetch_snapshots()
+        # t is accumulated by repeated "t += dt" (artery_network.py:946)
+        t_all = np.concatenate([[0.0], np.cumsum(np.full(N_cycles * Nt, self.dt))])
+        res = {'t': t_all[snaps['step']], 'step': snaps['step']}
+        for name in ('flow', 'area', 'pressure'):
+            if name in snaps:
+                res[name] = snaps[name][:, 0]
+        self.flags = flags
+        if write_output:
+            self._write_output(res)
+        return res
+
+    def _write_output(self, res):
+        out = self.sol['output_location']
+        for name in ('flow', 'area', 'pressure'):
+            if name not in res:
+                continue
+            for a in self.arteries:
+                if a is None:
+                    continue
+                f = _SeriesFile('%s/%s/%s_%i.xdmf' % (out, name, name, a.i))
+                f.write_series(res[name][:, a._k], name, res['t'])

@@ -1,0 +1,1196 @@
+// af_kernels.cu -- sm_100a kernels and the C ABI (include/arteryfe_b200.h) of
+// the artery.fe per-timestep network solve.
+//
+// Data layout in HBM (all FP64, SoA over vertices):
+//   A[2][nb*na*S], q[2][nb*na*S]   Un, ping-pong (cur / 1-cur), S = vertices padded to 32
+//   ves[nb*na]                     per-artery constants (struct Vessel)
+//   bc[nb*na*4]                    A_in, q_in, A_out, q_out   (the reference's BC holders)
+//   dex[nb*na], jx[nb*nj*18]       boundary step, junction unknowns (warm start)
+//   cellcoef[nt][9][S]             Gauss-point coefficients, tapered arteries only
+// One launch of k_boundary (all junctions + leaves of all networks) and one of
+// k_artery (one CTA per artery) make a time step; see DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/arteryfe_b200.h"
+#include "af_physics.cuh"
+
+using namespace af;
+
+// ---------------------------------------------------------------------------
+// device view
+// ---------------------------------------------------------------------------
+struct NetDev {
+  int nb, na, nj, nl, Nx, np, S, Nt;
+  double dt, theta;
+  const int* j_p;
+  const int* j_d1;
+  const int* j_d2;
+  const int* leaf_art;
+  const int* art_leaf;   // [na] leaf slot or -1
+  Vessel* ves;
+  double* A[2];
+  double* q[2];
+  double* bc;
+  double* dex;
+  double* jx;
+  const double* wk;      // [nb*nl*3]  R1, R2, CT
+  const double* q_ins;
+  int q_ins_per_net;
+  const int* coef_slot;  // [nb*na] index into cellcoef or -1
+  double* cellcoef;
+  int* art_its;
+  int* j_solves;
+  int* picard_its;
+  unsigned long long* totals;  // [3]
+  uint32_t* flags;             // [nb]
+  // solver constants
+  double newton_rtol, newton_atol;
+  int newton_max_it, junction_k_max, picard_k_max;
+  double junction_tol, picard_tol, cfl_margin;
+  // per-step counter log
+  int* log_art;
+  int* log_j;
+  int* log_p;
+};
+
+// ---------------------------------------------------------------------------
+// set-up: derived vessel constants, initial state, x0, coefficient tables
+// (ar:67-189, an:258-279, 434-473)
+// ---------------------------------------------------------------------------
+__global__ void k_setup_vessels(NetDev nd, const double* Ru, const double* Rd, const double* L, const double* k1,
+                                const double* k2, const double* k3, const double* rho, const double* Re,
+                                const double* db, const double* p0) {
+  int ba = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ba >= nd.nb * nd.na) return;
+  int b = ba / nd.na;
+  Vessel v;
+  v.Ru = Ru[ba]; v.Rd = Rd[ba]; v.L = L[ba];
+  v.dx = v.L / nd.Nx;
+  v.k1 = k1[b]; v.k2 = k2[b]; v.k3 = k3[b];
+  v.lr_over_L = log(v.Rd / v.Ru) / v.L;
+  v.rho = rho[b];
+  v.p0 = p0[b];
+  v.src_k = -2.0 * kSqrtPi / db[b] / Re[b];
+  v.rpi_dbRe = kSqrtPi / db[b] / Re[b];
+  v.tapered = (v.Rd != v.Ru) ? 1 : 0;
+  Coef c0 = coef_at(v, 0.0), cL = coef_at(v, v.L);
+  v.f0 = c0.f; v.A00 = c0.A0; v.fL = cL.f; v.A0L = cL.A0;
+  nd.ves[ba] = v;
+}
+
+__global__ void k_setup_state(NetDev nd, const double* q0) {
+  int ba = blockIdx.x;
+  const Vessel v = nd.ves[ba];
+  size_t off = (size_t)ba * nd.S;
+  for (int j = threadIdx.x; j < nd.S; j += blockDim.x) {
+    double A = 0.0, q = 0.0;
+    if (j < nd.np) {
+      A = coef_at(v, v.dx * j).A0;     // Un = (A0(x_j), q0)  (ar:154-157)
+      q = q0[ba];
+    }
+    nd.A[0][off + j] = A; nd.q[0][off + j] = q;
+    nd.A[1][off + j] = A; nd.q[1][off + j] = q;
+  }
+  if (threadIdx.x == 0) {
+    // BC holders (ar:171-187)
+    nd.bc[ba * 4 + 0] = v.A00;
+    nd.bc[ba * 4 + 1] = q0[ba];
+    nd.bc[ba * 4 + 2] = v.A0L;
+    nd.bc[ba * 4 + 3] = q0[ba];
+    nd.dex[ba] = v.dx;                 // ar:98
+  }
+  int slot = nd.coef_slot[ba];
+  if (slot >= 0) {
+    double* tab = nd.cellcoef + (size_t)slot * 9 * nd.S;
+    for (int e = threadIdx.x; e < nd.Nx; e += blockDim.x) {
+      CellCoef cc = cell_coef(v, v.dx * e, v.dx * (e + 1));
+      for (int g = 0; g < 3; ++g) {
+        tab[(0 + g) * nd.S + e] = cc.c1[g];
+        tab[(3 + g) * nd.S + e] = cc.t2[g];
+        tab[(6 + g) * nd.S + e] = cc.t3[g];
+      }
+    }
+  }
+}
+
+__global__ void k_setup_x(NetDev nd, const double* q0) {
+  // initial_x / define_x (an:434-473)
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nd.nb * nd.nj) return;
+  int b = t / nd.nj, j = t % nd.nj;
+  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+  double* x = nd.jx + (size_t)t * 18;
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    const Vessel& ves = nd.ves[ba];
+    double Ae = v == 0 ? ves.A0L : ves.A00;
+    for (int k = 0; k < 3; ++k) {
+      x[3 * v + k] = q0[ba];
+      x[9 + 3 * v + k] = Ae;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// boundary update: every junction (18-unknown Newton) and every leaf
+// (Windkessel Picard) of every network.  `lanes` threads per task, lane 0 works
+// (lanes = 32 gives every task its own warp for single networks; 1 packs
+// ensembles densely).                                    (an:740-786)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, int j, int log_slot) {
+  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+  const double* A = nd.A[cur];
+  const double* q = nd.q[cur];
+  // adjust_bifurcation_step (an:713-737)
+  double M = 1.0e300;
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    size_t off = (size_t)ba * nd.S;
+    double m = junction_cfl(nd.ves[ba], v, A + off, q + off, nd.Nx);
+    M = m < M ? m : M;          // NaN-propagation differs from python's min(); flagged below
+  }
+  double dex = (1.0 + nd.cfl_margin) * nd.dt / M;
+  JunctionCtx c;
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    size_t off = (size_t)ba * nd.S;
+    junction_prepare_vessel(c, v, nd.ves[ba], A + off, q + off, nd.Nx, nd.dt, dex);
+  }
+  double x[18];
+  double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
+  for (int i = 0; i < 18; ++i) x[i] = xg[i];
+  uint32_t fl = 0;
+  int solves = junction_newton(c, x, nd.junction_k_max, nd.junction_tol, &fl);
+  for (int i = 0; i < 18; ++i) xg[i] = x[i];
+  // set_inner_bc (an:762-764)
+  int bp = b * nd.na + ia[0], b1 = b * nd.na + ia[1], b2 = b * nd.na + ia[2];
+  nd.bc[bp * 4 + 2] = x[9];  nd.bc[bp * 4 + 3] = x[0];
+  nd.bc[b1 * 4 + 0] = x[12]; nd.bc[b1 * 4 + 1] = x[3];
+  nd.bc[b2 * 4 + 0] = x[15]; nd.bc[b2 * 4 + 1] = x[6];
+  nd.dex[bp] = dex;    // the value a non-leaf vessel holds after set_bcs
+  nd.j_solves[b * nd.nj + j] = solves;
+  if (log_slot >= 0) nd.log_j[(size_t)log_slot * nd.nb * nd.nj + b * nd.nj + j] = solves;
+  atomicAdd(&nd.totals[1], (unsigned long long)solves);
+  if (fl) atomicOr(&nd.flags[b], fl);
+}
+
+__device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int l, int log_slot) {
+  int ba = b * nd.na + nd.leaf_art[l];
+  size_t off = (size_t)ba * nd.S;
+  const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
+  WkResult r = windkessel(nd.ves[ba], nd.A[cur] + off, nd.q[cur] + off, nd.Nx, nd.dt, w[0], w[1], w[2],
+                          nd.picard_k_max, nd.picard_tol, nd.cfl_margin);
+  nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
+  nd.dex[ba] = r.dex;
+  nd.picard_its[b * nd.nl + l] = r.its;
+  if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
+  atomicAdd(&nd.totals[2], (unsigned long long)r.its);
+  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)AF_FLAG_PICARD_KMAX);
+}
+
+__global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
+  long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt % lanes) return;
+  long long task = gt / lanes;
+  long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
+  if (task < n_j) {
+    junction_task(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
+  } else if (task < n_j + n_l) {
+    task -= n_j;
+    leaf_task(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-artery Newton on the theta-scheme weak form: one CTA per artery.
+// Shared memory (doubles, S each): U(A,q) 2 | Un(A,q) 2 | Lo 4 | Dg 4 | Up 4 |
+// R 2 | D1 4 | Rr 2  = 24*S.                              (ar:233-251 + [3P])
+// ---------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  // fixed-order: lanes by xor-tree, warps in index order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < T / 32; ++k) s += red[k];
+  return s;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
+  extern __shared__ double sm[];
+  __shared__ double red[32];
+  const int S = nd.S, np = nd.np, ne = nd.Nx;
+  const int tid = threadIdx.x;
+  double* sA = sm;
+  double* sq = sA + S;
+  double* sAn = sq + S;
+  double* sqn = sAn + S;
+  double* Lo = sqn + S;
+  double* Dg = Lo + 4 * S;
+  double* Up = Dg + 4 * S;
+  double* R = Up + 4 * S;
+  double* D1 = R + 2 * S;
+  double* Rr = D1 + 4 * S;
+
+  const int ba = blockIdx.x + ba0;
+  const int b = ba / nd.na, a = ba % nd.na;
+  const Vessel v = nd.ves[ba];
+  const size_t off = (size_t)ba * S;
+  {
+    const double* gA = nd.A[cur] + off;
+    const double* gq = nd.q[cur] + off;
+    for (int i = tid; i < np; i += T) {
+      double x = gA[i], y = gq[i];
+      sA[i] = x; sAn[i] = x;
+      sq[i] = y; sqn[i] = y;
+    }
+  }
+  const bool root = (a == 0);
+  const bool leaf = nd.art_leaf[a] >= 0;
+  // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
+  double gAin = nd.bc[ba * 4 + 0], gqin = nd.bc[ba * 4 + 1];
+  const double gAout = nd.bc[ba * 4 + 2], gqout = nd.bc[ba * 4 + 3];
+  if (root && inlet_index >= 0) gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
+
+  ArteryConst ac;
+  ac.h = v.dx; ac.dt = nd.dt; ac.theta = nd.theta; ac.Kr = -v.src_k;
+  const double c1_0 = v.f0 * sqrt(v.A00), c1_L = v.fL * sqrt(v.A0L);
+  CellCoef ccu;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) { ccu.c1[g] = c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
+  const int slot = nd.coef_slot[ba];
+  const double* tab = slot >= 0 ? nd.cellcoef + (size_t)slot * 9 * S : nullptr;
+  __syncthreads();
+
+  int it = 0;
+  double r_first = 0.0;
+  uint32_t fl = 0;
+  for (;;) {
+    // ---- cells: residual + Jacobian blocks --------------------------------
+    for (int e = tid; e < ne; e += T) {
+      CellCoef cc = ccu;
+      if (tab) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          cc.c1[g] = tab[(0 + g) * S + e];
+          cc.t2[g] = tab[(3 + g) * S + e];
+          cc.t3[g] = tab[(6 + g) * S + e];
+        }
+      }
+      double rl[2], rr[2], b00[4], b01[4], b10[4], b11[4];
+      cell_assemble<true>(ac, cc, sA[e], sA[e + 1], sq[e], sq[e + 1], sAn[e], sAn[e + 1], sqn[e], sqn[e + 1], rl,
+                          rr, b00, b01, b10, b11);
+      R[e] = rl[0]; R[S + e] = rl[1];
+      Rr[e + 1] = rr[0]; Rr[S + e + 1] = rr[1];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        Dg[c * S + e] = b00[c];
+        Up[c * S + e] = b01[c];
+        Lo[c * S + e + 1] = b10[c];
+        D1[c * S + e + 1] = b11[c];
+      }
+    }
+    __syncthreads();
+    // ---- vertices: sum the two cells, facet terms, Dirichlet rows ----------
+    double part = 0.0;
+    for (int i = tid; i < np; i += T) {
+      double r0 = 0.0, r1 = 0.0, d[4] = {0.0, 0.0, 0.0, 0.0};
+      if (i < ne) {
+        r0 = R[i]; r1 = R[S + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] = Dg[c * S + i];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Up[c * S + i] = 0.0;
+      }
+      if (i > 0) {
+        r0 += Rr[i]; r1 += Rr[S + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] += D1[c * S + i];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Lo[c * S + i] = 0.0;
+      }
+      if (i == 0 || i == ne) {
+        double rq, dA, dq;
+        facet_term<true>(ac, i == 0 ? c1_0 : c1_L, sA[i], sq[i], sAn[i], sqn[i], rq, dA, dq);
+        r1 += rq; d[2] += dA; d[3] += dq;
+        // [3P] DirichletBC rows: residual = U - g, Jacobian row = identity
+        bool fixA = (i == 0) ? !root : true;
+        bool fixq = (i == 0) ? true : !leaf;
+        double gA = (i == 0) ? gAin : gAout, gq = (i == 0) ? gqin : gqout;
+        if (fixA) {
+          r0 = sA[i] - gA;
+          d[0] = 1.0; d[1] = 0.0;
+          Lo[0 * S + i] = 0.0; Lo[1 * S + i] = 0.0;
+          Up[0 * S + i] = 0.0; Up[1 * S + i] = 0.0;
+        }
+        if (fixq) {
+          r1 = sq[i] - gq;
+          d[2] = 0.0; d[3] = 1.0;
+          Lo[2 * S + i] = 0.0; Lo[3 * S + i] = 0.0;
+          Up[2 * S + i] = 0.0; Up[3 * S + i] = 0.0;
+        }
+      }
+      R[i] = r0; R[S + i] = r1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Dg[c * S + i] = d[c];
+      part += r0 * r0 + r1 * r1;
+    }
+    double r = sqrt(block_sum<T>(part, red));
+    // ---- [3P] NewtonSolver::converged ---------------------------------------
+    if (it == 0) r_first = r;
+    if (r / r_first < nd.newton_rtol || r < nd.newton_atol) break;
+    if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
+    if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
+    // ---- block cyclic reduction: J dU = R ----------------------------------
+    int s = 1;
+    for (; 2 * s - 1 < np; s *= 2) {
+      for (int i = 2 * s - 1 + tid * 2 * s; i < np; i += T * 2 * s) cr_forward(i, s, np, Lo, Dg, Up, R, S);
+      __syncthreads();
+    }
+    for (; s >= 1; s /= 2) {
+      for (int i = s - 1 + tid * 2 * s; i < np; i += T * 2 * s) cr_backward(i, s, np, Lo, Dg, Up, R, S);
+      __syncthreads();
+    }
+    for (int i = tid; i < np; i += T) {
+      sA[i] -= R[i];
+      sq[i] -= R[S + i];
+    }
+    __syncthreads();
+    ++it;
+  }
+  // update_solution (ar:247-251): Un <- U, into the other buffer
+  {
+    double* gA = nd.A[cur ^ 1] + off;
+    double* gq = nd.q[cur ^ 1] + off;
+    for (int i = tid; i < np; i += T) { gA[i] = sA[i]; gq[i] = sq[i]; }
+  }
+  if (tid == 0) {
+    nd.art_its[ba] = it;
+    if (log_slot >= 0) nd.log_art[(size_t)log_slot * nd.nb * nd.na + ba] = it;
+    atomicAdd(&nd.totals[0], (unsigned long long)it);
+    if (fl) atomicOr(&nd.flags[b], fl);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// snapshots (an:924-938) and update_pressure (ar:254-261)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double node_pressure(const Vessel& v, int j, double A) {
+  double f, A0;
+  if (v.tapered) {
+    Coef c = coef_at(v, v.dx * j);
+    f = c.f; A0 = c.A0;
+  } else {
+    f = v.f0; A0 = v.A00;
+  }
+  return v.p0 + f * (1.0 - sqrt(A0 / A));
+}
+
+__global__ void k_dump(NetDev nd, int cur, int fields, double* flow, double* area, double* pressure) {
+  int ba = blockIdx.x;
+  const Vessel v = nd.ves[ba];
+  size_t off = (size_t)ba * nd.S, o = (size_t)ba * nd.np;
+  for (int j = threadIdx.x; j < nd.np; j += blockDim.x) {
+    double A = nd.A[cur][off + j];
+    if (fields & AF_STORE_FLOW) flow[o + j] = nd.q[cur][off + j];
+    if (fields & AF_STORE_AREA) area[o + j] = A;
+    if (fields & AF_STORE_PRESSURE) pressure[o + j] = node_pressure(v, j, A);
+  }
+}
+
+__global__ void k_dump_outlet(NetDev nd, int cur, double* out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nd.nb * nd.nl) return;
+  int b = t / nd.nl, l = t % nd.nl;
+  int ba = b * nd.na + nd.leaf_art[l];
+  out[t] = outlet_pressure(nd.ves[ba], nd.A[cur][(size_t)ba * nd.S + nd.Nx]);
+}
+
+// state <-> dense host layout
+__global__ void k_pack(NetDev nd, int cur, double* A, double* q) {
+  int ba = blockIdx.x;
+  for (int j = threadIdx.x; j < nd.np; j += blockDim.x) {
+    A[(size_t)ba * nd.np + j] = nd.A[cur][(size_t)ba * nd.S + j];
+    q[(size_t)ba * nd.np + j] = nd.q[cur][(size_t)ba * nd.S + j];
+  }
+}
+
+__global__ void k_unpack(NetDev nd, int cur, const double* A, const double* q) {
+  int ba = blockIdx.x;
+  for (int j = threadIdx.x; j < nd.np; j += blockDim.x) {
+    nd.A[cur][(size_t)ba * nd.S + j] = A[(size_t)ba * nd.np + j];
+    nd.q[cur][(size_t)ba * nd.S + j] = q[(size_t)ba * nd.np + j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// one-thread evaluation kernels behind the fine-grained ABI entry points
+// ---------------------------------------------------------------------------
+// mode 0: flux/source at points x with states U -> out[n][3]; 1: u_half (x = x0, x1; U = U0, U1) -> out[2];
+// 2: CFL_term at x[0] with U[0..1] -> out[0]
+__global__ void k_eval_bc(NetDev nd, int ba, int mode, int n, const double* x, const double* U, double* out) {
+  const Vessel v = nd.ves[ba];
+  if (mode == 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      Coef c = coef_at(v, x[i]);
+      out[3 * i] = U[2 * i + 1];
+      out[3 * i + 1] = bc_flux2(c, U[2 * i], U[2 * i + 1]);
+      out[3 * i + 2] = bc_source2(v, c, U[2 * i], U[2 * i + 1]);
+    }
+  } else if (threadIdx.x == 0) {
+    if (mode == 1) {
+      u_half(v, nd.dt, x[0], x[1], U[0], U[1], U[2], U[3], out[0], out[1]);
+    } else {
+      out[0] = cfl_term(v, coef_at(v, x[0]), U[0], U[1]);
+    }
+  }
+}
+
+__global__ void k_eval_state(NetDev nd, int cur, int ba, int n, const double* x, double* out) {
+  size_t off = (size_t)ba * nd.S;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    interp_state(nd.A[cur] + off, nd.q[cur] + off, nd.Nx, nd.ves[ba].dx, x[i], out[2 * i], out[2 * i + 1]);
+}
+
+__global__ void k_eval_coef(NetDev nd, int ba, int n, const double* x, double* out) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    Coef c = coef_at(nd.ves[ba], x[i]);
+    out[4 * i] = c.f; out[4 * i + 1] = c.A0; out[4 * i + 2] = c.dfdr; out[4 * i + 3] = c.drdx;
+  }
+}
+
+// mode 0: cfl dex -> out[0]; 1: residual+jacobian at x (out = y[18], J[324]);
+// 2: newton (out = x[18], solves)
+__global__ void k_junction_debug(NetDev nd, int cur, int b, int j, int mode, const double* dex3, const double* xin,
+                                 int k_max, double tol, double* out) {
+  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+  const double* A = nd.A[cur];
+  const double* q = nd.q[cur];
+  if (mode == 0) {
+    double M = 1.0e300;
+    for (int v = 0; v < 3; ++v) {
+      int ba = b * nd.na + ia[v];
+      size_t off = (size_t)ba * nd.S;
+      double m = junction_cfl(nd.ves[ba], v, A + off, q + off, nd.Nx);
+      M = m < M ? m : M;
+    }
+    out[0] = (1.0 + nd.cfl_margin) * nd.dt / M;
+    return;
+  }
+  JunctionCtx c;
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    size_t off = (size_t)ba * nd.S;
+    junction_prepare_vessel(c, v, nd.ves[ba], A + off, q + off, nd.Nx, nd.dt, dex3[v]);
+  }
+  double x[18];
+  for (int i = 0; i < 18; ++i) x[i] = xin[i];
+  if (mode == 1) {
+    junction_residual(c, x, out);
+    junction_jacobian(c, x, out + 18, 18);
+  } else {
+    uint32_t fl = 0;
+    int solves = junction_newton(c, x, k_max, tol, &fl);
+    for (int i = 0; i < 18; ++i) out[i] = x[i];
+    out[18] = (double)solves;
+    out[19] = (double)fl;
+  }
+}
+
+__global__ void k_windkessel_debug(NetDev nd, int cur, int b, int l, int k_max, double tol, double* out) {
+  int ba = b * nd.na + nd.leaf_art[l];
+  size_t off = (size_t)ba * nd.S;
+  const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
+  WkResult r = windkessel(nd.ves[ba], nd.A[cur] + off, nd.q[cur] + off, nd.Nx, nd.dt, w[0], w[1], w[2], k_max, tol,
+                          nd.cfl_margin);
+  out[0] = r.A_out; out[1] = r.dex; out[2] = (double)r.its;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define AF_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      return fail(e_ == cudaErrorMemoryAllocation ? AF_ENOMEM : AF_ECUDA,                      \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+    }                                                                                          \
+  } while (0)
+
+struct af_net {
+  NetDev nd;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int cur = 0;
+  std::vector<void*> allocs;
+  // store
+  std::vector<uint8_t> mask;
+  int first_cycle = 0, max_snap = 0, fields = 0, n_snap = 0, snap_cap = 0;
+  double *s_flow = nullptr, *s_area = nullptr, *s_press = nullptr, *s_outlet = nullptr;
+  std::vector<int64_t> snap_step;
+  // log
+  int log_cap = 0, log_n = 0;
+  // scratch for the fine-grained calls
+  double* scratch = nullptr;      // device, 4096 doubles
+  int artery_threads = 256;
+  size_t artery_smem = 0;
+  int boundary_lanes = 32;
+  std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
+  int n_pending = 0;
+
+  template <typename Tp>
+  int dalloc(Tp** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(Tp));
+    if (e != cudaSuccess) return fail(AF_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = (Tp*)q;
+    return AF_OK;
+  }
+  template <typename Tp>
+  int upload(Tp** p, const Tp* h, size_t n) {
+    int rc = dalloc(p, n);
+    if (rc) return rc;
+    AF_CUDA(cudaMemcpyAsync(*p, h, n * sizeof(Tp), cudaMemcpyHostToDevice, stream));
+    return AF_OK;
+  }
+};
+
+extern "C" int af_version(void) { return AF_ABI_VERSION; }
+extern "C" const char* af_last_error(void) { return g_err.c_str(); }
+
+extern "C" void af_desc_defaults(af_desc* d) {
+  memset(d, 0, sizeof(*d));
+  d->abi_version = AF_ABI_VERSION;
+  d->n_networks = 1;
+  d->newton_rtol = 1e-9;
+  d->newton_atol = 1e-10;
+  d->newton_max_it = 1000;
+  d->junction_k_max = 30;
+  d->junction_tol = 1e-10;
+  d->picard_k_max = 100;
+  d->picard_tol = 1e-12;
+  d->cfl_margin = 0.05;
+}
+
+template <int T>
+static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot) {
+  k_artery<T><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
+  return cudaGetLastError();
+}
+
+template <int T>
+static cudaError_t prepare_artery(af_net* n) {
+  return cudaFuncSetAttribute(k_artery<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n->artery_smem);
+}
+
+static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot) {
+  switch (n->artery_threads) {
+    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot);
+    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot);
+    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot);
+    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot);
+  }
+}
+
+static cudaError_t run_boundary(const af_net* n, int log_slot) {
+  long long tasks = (long long)n->nd.nb * (n->nd.nj + n->nd.nl);
+  long long threads = tasks * n->boundary_lanes;
+  int block = n->boundary_lanes == 32 ? 32 : 64;
+  long long grid = (threads + block - 1) / block;
+  if (grid == 0) return cudaSuccess;
+  k_boundary<<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, n->boundary_lanes, log_slot);
+  return cudaGetLastError();
+}
+
+extern "C" int af_net_create(const af_desc* d, af_net** out) {
+  if (!d || !out) return fail(AF_EINVAL, "null argument");
+  *out = nullptr;
+  if (d->abi_version != AF_ABI_VERSION) return fail(AF_EINVAL, "af_desc.abi_version mismatch");
+  if (d->n_networks < 1 || d->n_arteries < 1 || d->Nx < 2 || d->Nt < 1 || d->n_junctions < 0 || d->n_leaves < 0)
+    return fail(AF_EINVAL, "bad sizes in af_desc");
+  if (d->Nx + 1 > 4096) return fail(AF_EINVAL, "Nx+1 > 4096 vertices per artery is not supported");
+  if (!d->k1 || !d->k2 || !d->k3 || !d->rho || !d->Re || !d->db || !d->p0 || !d->Ru || !d->Rd || !d->L || !d->q0 ||
+      !d->q_ins || (d->n_leaves && (!d->R1 || !d->R2 || !d->CT || !d->leaf_artery)) ||
+      (d->n_junctions && (!d->junction_parent || !d->junction_d1 || !d->junction_d2)))
+    return fail(AF_EINVAL, "null array in af_desc");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(AF_ENODEVICE, "no CUDA device: this library has no CPU path");
+  if (d->device < 0 || d->device >= ndev) return fail(AF_EINVAL, "bad device ordinal");
+  AF_CUDA(cudaSetDevice(d->device));
+
+  af_net* n = new (std::nothrow) af_net();
+  if (!n) return fail(AF_ENOMEM, "host allocation failed");
+  n->device = d->device;
+  if (d->stream) {
+    n->stream = (cudaStream_t)d->stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete n; return fail(AF_ECUDA, cudaGetErrorString(e)); }
+    n->own_stream = true;
+  }
+  NetDev& nd = n->nd;
+  memset(&nd, 0, sizeof(nd));
+  nd.nb = d->n_networks; nd.na = d->n_arteries; nd.nj = d->n_junctions; nd.nl = d->n_leaves;
+  nd.Nx = d->Nx; nd.np = d->Nx + 1; nd.S = (nd.np + 31) & ~31; nd.Nt = d->Nt;
+  nd.dt = d->dt; nd.theta = d->theta;
+  nd.newton_rtol = d->newton_rtol; nd.newton_atol = d->newton_atol; nd.newton_max_it = d->newton_max_it;
+  nd.junction_k_max = d->junction_k_max; nd.junction_tol = d->junction_tol;
+  nd.picard_k_max = d->picard_k_max; nd.picard_tol = d->picard_tol; nd.cfl_margin = d->cfl_margin;
+  nd.q_ins_per_net = d->q_ins_per_network;
+
+  const size_t nba = (size_t)nd.nb * nd.na;
+  int rc = AF_OK;
+#define AF_TRY(x) do { rc = (x); if (rc) { af_net_destroy(n); return rc; } } while (0)
+  // topology
+  std::vector<int> art_leaf(nd.na, -1);
+  for (int l = 0; l < nd.nl; ++l) {
+    int a = d->leaf_artery[l];
+    if (a < 0 || a >= nd.na) { af_net_destroy(n); return fail(AF_EINVAL, "leaf_artery out of range"); }
+    art_leaf[a] = l;
+  }
+  for (int j = 0; j < nd.nj; ++j) {
+    int ia[3] = {d->junction_parent[j], d->junction_d1[j], d->junction_d2[j]};
+    for (int v = 0; v < 3; ++v)
+      if (ia[v] < 0 || ia[v] >= nd.na) { af_net_destroy(n); return fail(AF_EINVAL, "junction index out of range"); }
+  }
+  int *dp, *dd1, *dd2, *dla, *dal;
+  AF_TRY(n->upload(&dp, d->junction_parent, nd.nj));
+  AF_TRY(n->upload(&dd1, d->junction_d1, nd.nj));
+  AF_TRY(n->upload(&dd2, d->junction_d2, nd.nj));
+  AF_TRY(n->upload(&dla, d->leaf_artery, nd.nl));
+  AF_TRY(n->upload(&dal, art_leaf.data(), nd.na));
+  nd.j_p = dp; nd.j_d1 = dd1; nd.j_d2 = dd2; nd.leaf_art = dla; nd.art_leaf = dal;
+  // parameters
+  double *k1, *k2, *k3, *rho, *Re, *db, *p0, *Ru, *Rd, *L, *q0, *qins;
+  AF_TRY(n->upload(&k1, d->k1, nd.nb)); AF_TRY(n->upload(&k2, d->k2, nd.nb)); AF_TRY(n->upload(&k3, d->k3, nd.nb));
+  AF_TRY(n->upload(&rho, d->rho, nd.nb)); AF_TRY(n->upload(&Re, d->Re, nd.nb)); AF_TRY(n->upload(&db, d->db, nd.nb));
+  AF_TRY(n->upload(&p0, d->p0, nd.nb));
+  AF_TRY(n->upload(&Ru, d->Ru, nba)); AF_TRY(n->upload(&Rd, d->Rd, nba)); AF_TRY(n->upload(&L, d->L, nba));
+  AF_TRY(n->upload(&q0, d->q0, nba));
+  AF_TRY(n->upload(&qins, d->q_ins, (size_t)nd.Nt * (nd.q_ins_per_net ? nd.nb : 1)));
+  nd.q_ins = qins;
+  std::vector<double> wk((size_t)nd.nb * nd.nl * 3);
+  for (size_t i = 0; i < (size_t)nd.nb * nd.nl; ++i) {
+    wk[3 * i] = d->R1[i]; wk[3 * i + 1] = d->R2[i]; wk[3 * i + 2] = d->CT[i];
+  }
+  double* dwk;
+  AF_TRY(n->upload(&dwk, wk.data(), wk.size()));
+  nd.wk = dwk;
+  // coefficient tables only for tapered arteries
+  std::vector<int> slot(nba, -1);
+  int n_tab = 0;
+  for (size_t i = 0; i < nba; ++i)
+    if (d->Rd[i] != d->Ru[i]) slot[i] = n_tab++;
+  int* dslot;
+  AF_TRY(n->upload(&dslot, slot.data(), nba));
+  nd.coef_slot = dslot;
+  AF_TRY(n->dalloc(&nd.cellcoef, (size_t)n_tab * 9 * nd.S));
+  // state
+  AF_TRY(n->dalloc(&nd.ves, nba));
+  for (int k = 0; k < 2; ++k) {
+    AF_TRY(n->dalloc(&nd.A[k], nba * nd.S));
+    AF_TRY(n->dalloc(&nd.q[k], nba * nd.S));
+  }
+  AF_TRY(n->dalloc(&nd.bc, nba * 4));
+  AF_TRY(n->dalloc(&nd.dex, nba));
+  AF_TRY(n->dalloc(&nd.jx, (size_t)nd.nb * nd.nj * 18));
+  AF_TRY(n->dalloc(&nd.art_its, nba));
+  AF_TRY(n->dalloc(&nd.j_solves, (size_t)nd.nb * nd.nj));
+  AF_TRY(n->dalloc(&nd.picard_its, (size_t)nd.nb * nd.nl));
+  AF_TRY(n->dalloc(&nd.totals, 3));
+  AF_TRY(n->dalloc(&nd.flags, nd.nb));
+  AF_TRY(n->dalloc(&n->scratch, 4096));
+  cudaMemsetAsync(nd.art_its, 0, nba * sizeof(int), n->stream);
+  cudaMemsetAsync(nd.j_solves, 0, (size_t)nd.nb * nd.nj * sizeof(int) + 0, n->stream);
+  cudaMemsetAsync(nd.picard_its, 0, (size_t)nd.nb * nd.nl * sizeof(int) + 0, n->stream);
+  cudaMemsetAsync(nd.totals, 0, 3 * sizeof(unsigned long long), n->stream);
+  cudaMemsetAsync(nd.flags, 0, nd.nb * sizeof(uint32_t), n->stream);
+
+  n->pending.assign(nba, 0);
+  // launch configuration
+  n->artery_threads = nd.np <= 64 ? 64 : (nd.np <= 160 ? 128 : (nd.np <= 640 ? 256 : 512));
+  n->artery_smem = (size_t)24 * nd.S * sizeof(double);
+  n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
+  cudaError_t e;
+  switch (n->artery_threads) {
+    case 64: e = prepare_artery<64>(n); break;
+    case 128: e = prepare_artery<128>(n); break;
+    case 256: e = prepare_artery<256>(n); break;
+    default: e = prepare_artery<512>(n); break;
+  }
+  if (e != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("artery kernel smem: ") + cudaGetErrorString(e)); }
+
+  k_setup_vessels<<<(unsigned)((nba + 127) / 128), 128, 0, n->stream>>>(nd, Ru, Rd, L, k1, k2, k3, rho, Re, db, p0);
+  k_setup_state<<<(unsigned)nba, 128, 0, n->stream>>>(nd, q0);
+  if (nd.nj) k_setup_x<<<(unsigned)(((size_t)nd.nb * nd.nj + 127) / 128), 128, 0, n->stream>>>(nd, q0);
+  e = cudaStreamSynchronize(n->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("set-up kernels: ") + cudaGetErrorString(e)); }
+#undef AF_TRY
+  *out = n;
+  return AF_OK;
+}
+
+extern "C" void af_net_destroy(af_net* n) {
+  if (!n) return;
+  cudaSetDevice(n->device);
+  if (n->stream) cudaStreamSynchronize(n->stream);
+  for (void* p : n->allocs) cudaFree(p);
+  if (n->own_stream && n->stream) cudaStreamDestroy(n->stream);
+  delete n;
+}
+
+static int check(af_net* n) {
+  if (!n) return fail(AF_EINVAL, "null handle");
+  AF_CUDA(cudaSetDevice(n->device));
+  return AF_OK;
+}
+
+extern "C" int af_net_sync(af_net* n) {
+  int rc = check(n);
+  if (rc) return rc;
+  AF_CUDA(cudaStreamSynchronize(n->stream));
+  AF_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+static int take_snapshot(af_net* n, int64_t g) {
+  if (n->n_snap >= n->max_snap) return AF_OK;
+  const NetDev& nd = n->nd;
+  size_t per = (size_t)nd.nb * nd.na * nd.np;
+  if (n->fields & (AF_STORE_FLOW | AF_STORE_AREA | AF_STORE_PRESSURE)) {
+    k_dump<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, n->fields,
+                                                  n->s_flow ? n->s_flow + per * n->n_snap : nullptr,
+                                                  n->s_area ? n->s_area + per * n->n_snap : nullptr,
+                                                  n->s_press ? n->s_press + per * n->n_snap : nullptr);
+    AF_CUDA(cudaGetLastError());
+  }
+  if (n->fields & AF_STORE_OUTLET_PRESSURE) {
+    size_t pl = (size_t)nd.nb * nd.nl;
+    k_dump_outlet<<<(unsigned)((pl + 127) / 128), 128, 0, n->stream>>>(nd, n->cur, n->s_outlet + pl * n->n_snap);
+    AF_CUDA(cudaGetLastError());
+  }
+  n->snap_step.push_back(g);
+  n->n_snap++;
+  return AF_OK;
+}
+
+extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (n_first < 0 || n_steps < 0) return fail(AF_EINVAL, "negative step range");
+  if (n->n_pending) return fail(AF_ESTATE, "arteries with a pending solve: call af_artery_update first");
+  const int Nt = n->nd.Nt;
+  for (int64_t g = n_first; g < n_first + n_steps; ++g) {
+    int step = (int)(g % Nt);
+    int64_t cycle = g / Nt;
+    if (n->max_snap && cycle >= n->first_cycle && n->mask[step]) {
+      rc = take_snapshot(n, g);
+      if (rc) return rc;
+    }
+    int log_slot = (n->log_n < n->log_cap) ? n->log_n++ : -1;
+    int inlet = (step + 1) % Nt;                       // an:916
+    AF_CUDA(run_boundary(n, log_slot));
+    AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot));
+    n->cur ^= 1;
+  }
+  return AF_OK;
+}
+
+extern "C" int af_phase_boundary(af_net* n) {
+  int rc = check(n);
+  if (rc) return rc;
+  AF_CUDA(run_boundary(n, -1));
+  return AF_OK;
+}
+
+extern "C" int af_phase_arteries(af_net* n, int32_t inlet_index) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (inlet_index < -1 || inlet_index >= n->nd.Nt) return fail(AF_EINVAL, "inlet_index out of range");
+  if (n->n_pending) return fail(AF_ESTATE, "arteries with a pending solve: call af_artery_update first");
+  AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet_index, -1));
+  n->cur ^= 1;
+  return AF_OK;
+}
+
+extern "C" int af_artery_solve(af_net* n, int32_t network, int32_t artery) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (network < 0 || network >= n->nd.nb || artery < 0 || artery >= n->nd.na)
+    return fail(AF_EINVAL, "network/artery index out of range");
+  int ba = network * n->nd.na + artery;
+  AF_CUDA(run_artery(n, ba, 1, -1, -1));      // U -> the other buffer, Un untouched
+  if (!n->pending[ba]) { n->pending[ba] = 1; n->n_pending++; }
+  return AF_OK;
+}
+
+extern "C" int af_artery_update(af_net* n, int32_t network, int32_t artery) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (network < 0 || network >= n->nd.nb || artery < 0 || artery >= n->nd.na)
+    return fail(AF_EINVAL, "network/artery index out of range");
+  int ba = network * n->nd.na + artery;
+  if (!n->pending[ba]) return AF_OK;          // U == Un already
+  size_t off = (size_t)ba * n->nd.S, bytes = (size_t)n->nd.S * sizeof(double);
+  AF_CUDA(cudaMemcpyAsync(n->nd.A[n->cur] + off, n->nd.A[n->cur ^ 1] + off, bytes, cudaMemcpyDeviceToDevice, n->stream));
+  AF_CUDA(cudaMemcpyAsync(n->nd.q[n->cur] + off, n->nd.q[n->cur ^ 1] + off, bytes, cudaMemcpyDeviceToDevice, n->stream));
+  n->pending[ba] = 0;
+  n->n_pending--;
+  return AF_OK;
+}
+
+extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t first_cycle, int32_t max_snapshots,
+                                int32_t fields) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!step_mask || max_snapshots < 1 || !fields) return fail(AF_EINVAL, "bad store configuration");
+  const NetDev& nd = n->nd;
+  // (re)configuration: buffers are reused when they are large enough
+  if (fields != n->fields || max_snapshots > n->snap_cap) {
+    size_t per = (size_t)nd.nb * nd.na * nd.np;
+    n->s_flow = n->s_area = n->s_press = n->s_outlet = nullptr;
+    if (fields & AF_STORE_FLOW) { rc = n->dalloc(&n->s_flow, per * max_snapshots); if (rc) return rc; }
+    if (fields & AF_STORE_AREA) { rc = n->dalloc(&n->s_area, per * max_snapshots); if (rc) return rc; }
+    if (fields & AF_STORE_PRESSURE) { rc = n->dalloc(&n->s_press, per * max_snapshots); if (rc) return rc; }
+    if (fields & AF_STORE_OUTLET_PRESSURE) {
+      rc = n->dalloc(&n->s_outlet, (size_t)nd.nb * nd.nl * max_snapshots);
+      if (rc) return rc;
+    }
+    n->snap_cap = max_snapshots;
+  }
+  n->mask.assign(step_mask, step_mask + nd.Nt);
+  n->first_cycle = first_cycle;
+  n->fields = fields;
+  n->max_snap = max_snapshots;
+  n->n_snap = 0;
+  n->snap_step.clear();
+  return AF_OK;
+}
+
+extern "C" int af_net_snapshot_count(af_net* n, int32_t* count) {
+  if (!n || !count) return fail(AF_EINVAL, "null argument");
+  *count = n->n_snap;
+  return AF_OK;
+}
+
+extern "C" int af_net_fetch_snapshots(af_net* n, double* flow, double* area, double* pressure,
+                                      double* outlet_pressure, int64_t* step) {
+  int rc = check(n);
+  if (rc) return rc;
+  const NetDev& nd = n->nd;
+  size_t per = (size_t)nd.nb * nd.na * nd.np * n->n_snap * sizeof(double);
+  if (flow) { if (!n->s_flow) return fail(AF_ESTATE, "flow not stored"); AF_CUDA(cudaMemcpyAsync(flow, n->s_flow, per, cudaMemcpyDeviceToHost, n->stream)); }
+  if (area) { if (!n->s_area) return fail(AF_ESTATE, "area not stored"); AF_CUDA(cudaMemcpyAsync(area, n->s_area, per, cudaMemcpyDeviceToHost, n->stream)); }
+  if (pressure) { if (!n->s_press) return fail(AF_ESTATE, "pressure not stored"); AF_CUDA(cudaMemcpyAsync(pressure, n->s_press, per, cudaMemcpyDeviceToHost, n->stream)); }
+  if (outlet_pressure) {
+    if (!n->s_outlet) return fail(AF_ESTATE, "outlet pressure not stored");
+    AF_CUDA(cudaMemcpyAsync(outlet_pressure, n->s_outlet, (size_t)nd.nb * nd.nl * n->n_snap * sizeof(double),
+                            cudaMemcpyDeviceToHost, n->stream));
+  }
+  AF_CUDA(cudaStreamSynchronize(n->stream));
+  if (step) for (int i = 0; i < n->n_snap; ++i) step[i] = n->snap_step[i];
+  return AF_OK;
+}
+
+extern "C" int af_net_outlet_pressure_d(af_net* n, double** ptr_d) {
+  if (!n || !ptr_d) return fail(AF_EINVAL, "null argument");
+  if (!n->s_outlet) return fail(AF_ESTATE, "outlet pressure not stored");
+  *ptr_d = n->s_outlet;
+  return AF_OK;
+}
+
+// dense <-> padded copies go through a temporary device buffer
+static int with_dense(af_net* n, double* hA, double* hq, const double* cA, const double* cq, bool to_host) {
+  const NetDev& nd = n->nd;
+  size_t cnt = (size_t)nd.nb * nd.na * nd.np;
+  double *dA = nullptr, *dq = nullptr;
+  AF_CUDA(cudaMalloc(&dA, cnt * sizeof(double)));
+  cudaError_t e = cudaMalloc(&dq, cnt * sizeof(double));
+  if (e != cudaSuccess) { cudaFree(dA); return fail(AF_ENOMEM, cudaGetErrorString(e)); }
+  if (to_host) {
+    k_pack<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, dA, dq);
+    cudaMemcpyAsync(hA, dA, cnt * sizeof(double), cudaMemcpyDeviceToHost, n->stream);
+    cudaMemcpyAsync(hq, dq, cnt * sizeof(double), cudaMemcpyDeviceToHost, n->stream);
+  } else {
+    cudaMemcpyAsync(dA, cA, cnt * sizeof(double), cudaMemcpyHostToDevice, n->stream);
+    cudaMemcpyAsync(dq, cq, cnt * sizeof(double), cudaMemcpyHostToDevice, n->stream);
+    k_unpack<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, dA, dq);
+    // the Newton initial guess U is Un (ar:158), nothing else to reset
+  }
+  e = cudaStreamSynchronize(n->stream);
+  cudaFree(dA); cudaFree(dq);
+  if (e != cudaSuccess) return fail(AF_ECUDA, cudaGetErrorString(e));
+  return AF_OK;
+}
+
+extern "C" int af_net_get_state(af_net* n, double* A, double* q) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!A || !q) return fail(AF_EINVAL, "null argument");
+  return with_dense(n, A, q, nullptr, nullptr, true);
+}
+
+extern "C" int af_net_set_state(af_net* n, const double* A, const double* q) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!A || !q) return fail(AF_EINVAL, "null argument");
+  std::fill(n->pending.begin(), n->pending.end(), (uint8_t)0);   // U.assign(Un) (ar:158)
+  n->n_pending = 0;
+  return with_dense(n, nullptr, nullptr, A, q, false);
+}
+
+extern "C" int af_net_get_pressure(af_net* n, double* p) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!p) return fail(AF_EINVAL, "null argument");
+  const NetDev& nd = n->nd;
+  size_t cnt = (size_t)nd.nb * nd.na * nd.np;
+  double* dp = nullptr;
+  AF_CUDA(cudaMalloc(&dp, cnt * sizeof(double)));
+  k_dump<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, AF_STORE_PRESSURE, nullptr, nullptr, dp);
+  cudaMemcpyAsync(p, dp, cnt * sizeof(double), cudaMemcpyDeviceToHost, n->stream);
+  cudaError_t e = cudaStreamSynchronize(n->stream);
+  cudaFree(dp);
+  if (e != cudaSuccess) return fail(AF_ECUDA, cudaGetErrorString(e));
+  return AF_OK;
+}
+
+template <typename Tp>
+static int d2h(af_net* n, Tp* host, const Tp* dev, size_t cnt) {
+  if (!host) return AF_OK;
+  AF_CUDA(cudaMemcpyAsync(host, dev, cnt * sizeof(Tp), cudaMemcpyDeviceToHost, n->stream));
+  AF_CUDA(cudaStreamSynchronize(n->stream));
+  return AF_OK;
+}
+
+template <typename Tp>
+static int h2d(af_net* n, Tp* dev, const Tp* host, size_t cnt) {
+  if (!host) return fail(AF_EINVAL, "null argument");
+  AF_CUDA(cudaMemcpyAsync(dev, host, cnt * sizeof(Tp), cudaMemcpyHostToDevice, n->stream));
+  AF_CUDA(cudaStreamSynchronize(n->stream));
+  return AF_OK;
+}
+
+extern "C" int af_net_get_bc(af_net* n, double* bc) {
+  int rc = check(n);
+  return rc ? rc : d2h(n, bc, n->nd.bc, (size_t)n->nd.nb * n->nd.na * 4);
+}
+extern "C" int af_net_set_bc(af_net* n, const double* bc) {
+  int rc = check(n);
+  return rc ? rc : h2d(n, n->nd.bc, bc, (size_t)n->nd.nb * n->nd.na * 4);
+}
+extern "C" int af_net_get_dex(af_net* n, double* dex) {
+  int rc = check(n);
+  return rc ? rc : d2h(n, dex, n->nd.dex, (size_t)n->nd.nb * n->nd.na);
+}
+extern "C" int af_net_set_dex(af_net* n, const double* dex) {
+  int rc = check(n);
+  return rc ? rc : h2d(n, n->nd.dex, dex, (size_t)n->nd.nb * n->nd.na);
+}
+extern "C" int af_net_get_junction_x(af_net* n, double* x) {
+  int rc = check(n);
+  return rc ? rc : d2h(n, x, n->nd.jx, (size_t)n->nd.nb * n->nd.nj * 18);
+}
+extern "C" int af_net_set_junction_x(af_net* n, const double* x) {
+  int rc = check(n);
+  return rc ? rc : h2d(n, n->nd.jx, x, (size_t)n->nd.nb * n->nd.nj * 18);
+}
+extern "C" int af_net_get_counters(af_net* n, int32_t* artery_its, int32_t* junction_solves, int32_t* picard_its) {
+  int rc = check(n);
+  if (rc) return rc;
+  const NetDev& nd = n->nd;
+  if ((rc = d2h(n, artery_its, nd.art_its, (size_t)nd.nb * nd.na))) return rc;
+  if ((rc = d2h(n, junction_solves, nd.j_solves, (size_t)nd.nb * nd.nj))) return rc;
+  return d2h(n, picard_its, nd.picard_its, (size_t)nd.nb * nd.nl);
+}
+extern "C" int af_net_get_totals(af_net* n, int64_t totals[3]) {
+  int rc = check(n);
+  return rc ? rc : d2h(n, (unsigned long long*)totals, n->nd.totals, 3);
+}
+extern "C" int af_net_get_flags(af_net* n, uint32_t* flags) {
+  int rc = check(n);
+  return rc ? rc : d2h(n, flags, n->nd.flags, (size_t)n->nd.nb);
+}
+
+extern "C" int af_net_set_counter_log(af_net* n, int32_t capacity) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (n->log_cap) return fail(AF_ESTATE, "counter log already configured");
+  if (capacity < 1) return fail(AF_EINVAL, "capacity < 1");
+  NetDev& nd = n->nd;
+  if ((rc = n->dalloc(&nd.log_art, (size_t)capacity * nd.nb * nd.na))) return rc;
+  if ((rc = n->dalloc(&nd.log_j, (size_t)capacity * nd.nb * nd.nj))) return rc;
+  if ((rc = n->dalloc(&nd.log_p, (size_t)capacity * nd.nb * nd.nl))) return rc;
+  n->log_cap = capacity;
+  n->log_n = 0;
+  return AF_OK;
+}
+
+extern "C" int af_net_fetch_counter_log(af_net* n, int32_t* n_logged, int32_t* artery_its, int32_t* junction_solves,
+                                        int32_t* picard_its) {
+  int rc = check(n);
+  if (rc) return rc;
+  const NetDev& nd = n->nd;
+  if (n_logged) *n_logged = n->log_n;
+  if ((rc = d2h(n, artery_its, nd.log_art, (size_t)n->log_n * nd.nb * nd.na))) return rc;
+  if ((rc = d2h(n, junction_solves, nd.log_j, (size_t)n->log_n * nd.nb * nd.nj))) return rc;
+  return d2h(n, picard_its, nd.log_p, (size_t)n->log_n * nd.nb * nd.nl);
+}
+
+// ---- fine-grained evaluations ------------------------------------------------
+static int check_ba(af_net* n, int network, int artery) {
+  if (network < 0 || network >= n->nd.nb || artery < 0 || artery >= n->nd.na)
+    return fail(AF_EINVAL, "network/artery index out of range");
+  return AF_OK;
+}
+
+extern "C" int af_eval_state(af_net* n, int32_t network, int32_t artery, int32_t which, int32_t cnt, const double* x,
+                             double* out) {
+  int rc = check(n);
+  if (rc) return rc;
+  if ((rc = check_ba(n, network, artery))) return rc;
+  if (cnt < 0 || cnt > 1024 || !x || !out) return fail(AF_EINVAL, "bad point list (max 1024)");
+  int ba = network * n->nd.na + artery;
+  int buf = (which == 1 && n->pending[ba]) ? (n->cur ^ 1) : n->cur;   // U == Un unless a solve is pending
+  AF_CUDA(cudaMemcpyAsync(n->scratch, x, cnt * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  k_eval_state<<<1, 64, 0, n->stream>>>(n->nd, buf, ba, cnt, n->scratch, n->scratch + 1024);
+  AF_CUDA(cudaGetLastError());
+  return d2h(n, out, n->scratch + 1024, (size_t)cnt * 2);
+}
+
+extern "C" int af_eval_coefficients(af_net* n, int32_t network, int32_t artery, int32_t cnt, const double* x,
+                                    double* out) {
+  int rc = check(n);
+  if (rc) return rc;
+  if ((rc = check_ba(n, network, artery))) return rc;
+  if (cnt < 0 || cnt > 512 || !x || !out) return fail(AF_EINVAL, "bad point list (max 512)");
+  AF_CUDA(cudaMemcpyAsync(n->scratch, x, cnt * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  k_eval_coef<<<1, 64, 0, n->stream>>>(n->nd, network * n->nd.na + artery, cnt, n->scratch, n->scratch + 1024);
+  AF_CUDA(cudaGetLastError());
+  return d2h(n, out, n->scratch + 1024, (size_t)cnt * 4);
+}
+
+extern "C" int af_eval_flux_source(af_net* n, int32_t network, int32_t artery, int32_t cnt, const double* x,
+                                   const double* U, double* out) {
+  int rc = check(n);
+  if (rc) return rc;
+  if ((rc = check_ba(n, network, artery))) return rc;
+  if (cnt < 0 || cnt > 256 || !x || !U || !out) return fail(AF_EINVAL, "bad point list (max 256)");
+  double* s = n->scratch;
+  AF_CUDA(cudaMemcpyAsync(s, x, cnt * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  AF_CUDA(cudaMemcpyAsync(s + 256, U, 2 * cnt * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  k_eval_bc<<<1, 64, 0, n->stream>>>(n->nd, network * n->nd.na + artery, 0, cnt, s, s + 256, s + 1024);
+  AF_CUDA(cudaGetLastError());
+  return d2h(n, out, s + 1024, (size_t)cnt * 3);
+}
+
+extern "C" int af_eval_u_half(af_net* n, int32_t network, int32_t artery, double x0, double x1, const double U0[2],
+                              const double U1[2], double out[2]) {
+  int rc = check(n);
+  if (rc) return rc;
+  if ((rc = check_ba(n, network, artery))) return rc;
+  if (!U0 || !U1 || !out) return fail(AF_EINVAL, "null argument");
+  double h[6] = {x0, x1, U0[0], U0[1], U1[0], U1[1]};
+  double* s = n->scratch;
+  AF_CUDA(cudaMemcpyAsync(s, h, sizeof(h), cudaMemcpyHostToDevice, n->stream));
+  k_eval_bc<<<1, 32, 0, n->stream>>>(n->nd, network * n->nd.na + artery, 1, 1, s, s + 2, s + 1024);
+  AF_CUDA(cudaGetLastError());
+  return d2h(n, out, s + 1024, 2);
+}
+
+extern "C" int af_eval_cfl_term(af_net* n, int32_t network, int32_t artery, double x, double A, double q, double* M) {
+  int rc = check(n);
+  if (rc) return rc;
+  if ((rc = check_ba(n, network, artery))) return rc;
+  if (!M) return fail(AF_EINVAL, "null argument");
+  double h[3] = {x, A, q};
+  double* s = n->scratch;
+  AF_CUDA(cudaMemcpyAsync(s, h, sizeof(h), cudaMemcpyHostToDevice, n->stream));
+  k_eval_bc<<<1, 32, 0, n->stream>>>(n->nd, network * n->nd.na + artery, 2, 1, s, s + 1, s + 1024);
+  AF_CUDA(cudaGetLastError());
+  return d2h(n, M, s + 1024, 1);
+}
+
+static int junction_call(af_net* n, int network, int junction, int mode, const double* dex3, const double* x,
+                         int k_max, double tol, double* host_out, size_t n_out) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (network < 0 || network >= n->nd.nb || junction < 0 || junction >= n->nd.nj)
+    return fail(AF_EINVAL, "network/junction index out of range");
+  double* s = n->scratch;
+  if (dex3) AF_CUDA(cudaMemcpyAsync(s, dex3, 3 * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  if (x) AF_CUDA(cudaMemcpyAsync(s + 8, x, 18 * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  k_junction_debug<<<1, 1, 0, n->stream>>>(n->nd, n->cur, network, junction, mode, s, s + 8, k_max, tol, s + 64);
+  AF_CUDA(cudaGetLastError());
+  return d2h(n, host_out, s + 64, n_out);
+}
+
+extern "C" int af_junction_cfl_dex(af_net* n, int32_t network, int32_t junction, double* dex) {
+  if (!dex) return fail(AF_EINVAL, "null argument");
+  return junction_call(n, network, junction, 0, nullptr, nullptr, 0, 0.0, dex, 1);
+}
+
+extern "C" int af_junction_eval(af_net* n, int32_t network, int32_t junction, const double dex[3], const double* x,
+                                double* y, double* J) {
+  if (!dex || !x) return fail(AF_EINVAL, "null argument");
+  double buf[18 + 324];
+  int rc = junction_call(n, network, junction, 1, dex, x, 0, 0.0, buf, 18 + 324);
+  if (rc) return rc;
+  if (y) memcpy(y, buf, 18 * sizeof(double));
+  if (J) memcpy(J, buf + 18, 324 * sizeof(double));
+  return AF_OK;
+}
+
+extern "C" int af_junction_newton(af_net* n, int32_t network, int32_t junction, const double dex[3], double* x,
+                                  int32_t k_max, double tol, int32_t* solves) {
+  if (!dex || !x) return fail(AF_EINVAL, "null argument");
+  double buf[20];
+  int rc = junction_call(n, network, junction, 2, dex, x, k_max, tol, buf, 20);
+  if (rc) return rc;
+  memcpy(x, buf, 18 * sizeof(double));
+  if (solves) *solves = (int32_t)buf[18];
+  return AF_OK;
+}
+
+extern "C" int af_windkessel(af_net* n, int32_t network, int32_t leaf, int32_t k_max, double tol, double* A_out,
+                             double* dex, int32_t* its) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (network < 0 || network >= n->nd.nb || leaf < 0 || leaf >= n->nd.nl)
+    return fail(AF_EINVAL, "network/leaf index out of range");
+  k_windkessel_debug<<<1, 1, 0, n->stream>>>(n->nd, n->cur, network, leaf, k_max, tol, n->scratch);
+  AF_CUDA(cudaGetLastError());
+  double buf[3];
+  if ((rc = d2h(n, buf, n->scratch, 3))) return rc;
+  if (A_out) *A_out = buf[0];
+  if (dex) *dex = buf[1];
+  if (its) *its = (int32_t)buf[2];
+  return AF_OK;
+}

@@ -1,0 +1,597 @@
+// af_physics.cuh -- per-thread FP64 math of the artery.fe network solve.
+//
+// Everything here is a small inline function operating on registers / caller
+// supplied arrays; the kernels in af_kernels.cu decide which thread runs which
+// piece.  References are to /root/reference/arteryfe (an = artery_network.py,
+// ar = artery.py); [3P] marks FEniCS 2017.2.0 semantics.
+//
+// The functions are AF_HD so that tests/host_harness can compile this header
+// with g++ and unit-test the formulas in the CPU-only build container.  The
+// product library (libarteryfe_b200.so) only ever executes them on the device.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define AF_HD __host__ __device__ __forceinline__
+#else
+#define AF_HD inline
+#endif
+
+namespace af {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kSqrtPi = 1.7724538509055159;   // == (double)sqrt((double)pi)
+constexpr double kDolfinEps = 3.0e-16;           // [3P] DOLFIN_EPS
+// [3P] 3-point Gauss-Legendre on [0,1] (quadrature_degree = 4, ar:9)
+constexpr double kXi0 = 0.11270166537925831148;  // 1/2 - sqrt(3/5)/2
+constexpr double kXi1 = 0.5;
+constexpr double kXi2 = 0.88729833462074168852;
+constexpr double kW0 = 5.0 / 18.0, kW1 = 8.0 / 18.0, kW2 = 5.0 / 18.0;
+
+}  // namespace af
+// status bits (per network); same values as include/arteryfe_b200.h
+#ifndef AF_FLAG_ARTERY_NOCONV
+#define AF_FLAG_ARTERY_NOCONV 1u
+#define AF_FLAG_JUNCTION_KMAX 2u
+#define AF_FLAG_PICARD_KMAX 4u
+#define AF_FLAG_NONFINITE 8u
+#define AF_FLAG_SINGULAR 16u
+#endif
+namespace af {
+
+// ---------------------------------------------------------------------------
+// vessel constants and the analytic Expressions  (ar:110-118)
+// ---------------------------------------------------------------------------
+struct Vessel {
+  double Ru, Rd, L, dx;
+  double k1, k2, k3;
+  double lr_over_L;     // log(Rd/Ru)/L                      (ar:117-118)
+  double rho;           // dimensional, used by CFL_term     (ar:322)
+  double p0;
+  double src_k;         // -2*sqrt(pi)/db/Re                 (an:322)
+  double rpi_dbRe;      // sqrt(pi)/db/Re                    (an:639)
+  int32_t tapered;      // Rd != Ru
+  // Expression values cached for untapered vessels and for the two ends
+  double f0, A00, fL, A0L;
+};
+
+struct Coef {
+  double f, A0, dfdr, drdx;
+};
+
+AF_HD Coef coef_at(const Vessel& v, double x) {
+  Coef c;
+  // r0 = Ru*pow(Rd/Ru, x/L); pow(1, y) == 1 exactly, so the untapered branch
+  // only skips work.
+  double r0 = v.tapered ? v.Ru * pow(v.Rd / v.Ru, x / v.L) : v.Ru;
+  double e = exp(v.k2 * r0);
+  c.A0 = kPi * (r0 * r0);
+  c.f = 4.0 / 3.0 * (v.k1 * e + v.k3);
+  c.dfdr = 4.0 / 3.0 * v.k1 * v.k2 * e;
+  c.drdx = v.lr_over_L * r0;
+  return c;
+}
+
+// P1 point evaluation of (A, q) on the uniform mesh x_j = j*dx  ([3P] a15)
+AF_HD void interp_state(const double* A, const double* q, int Nx, double dx, double x,
+                        double& Ax, double& qx) {
+  int j = (int)floor(x / dx);
+  j = j < 0 ? 0 : (j > Nx - 1 ? Nx - 1 : j);
+  double xi = (x - j * dx) / dx;
+  Ax = A[j] * (1.0 - xi) + A[j + 1] * xi;
+  qx = q[j] * (1.0 - xi) + q[j + 1] * xi;
+}
+
+// ---------------------------------------------------------------------------
+// boundary-condition physics  (an:282-358)
+// ---------------------------------------------------------------------------
+// flux: F = (q, q^2 + f*sqrt(A0*A))   -- no "/A" (an:300)
+AF_HD double bc_flux2(const Coef& c, double A, double q) { return q * q + c.f * sqrt(c.A0 * A); }
+
+// source: S2 (an:322-325)
+AF_HD double bc_source2(const Vessel& v, const Coef& c, double A, double q) {
+  double sA = sqrt(A);
+  return v.src_k * q / sA + (2.0 * sA * (kSqrtPi * c.f + sqrt(c.A0) * c.dfdr) - A * c.dfdr) * c.drdx;
+}
+
+// compute_U_half (an:329-358): note dt/(x1-x0) and dt/4
+AF_HD void u_half(const Vessel& v, double dt, double x0, double x1, double A0s, double q0s, double A1s,
+                  double q1s, double& Ah, double& qh) {
+  Coef c0 = coef_at(v, x0), c1 = coef_at(v, x1);
+  double F0 = bc_flux2(c0, A0s, q0s), F1 = bc_flux2(c1, A1s, q1s);
+  double S0 = bc_source2(v, c0, A0s, q0s), S1 = bc_source2(v, c1, A1s, q1s);
+  double r = dt / (x1 - x0);
+  Ah = (A0s + A1s) / 2.0 - r * (q1s - q0s);
+  qh = (q0s + q1s) / 2.0 - r * (F1 - F0) + dt / 4.0 * (S0 + S1);
+}
+
+// CFL_term (ar:304-325)
+AF_HD double cfl_term(const Vessel& v, const Coef& c, double A, double q) {
+  double w = sqrt(c.f / 2.0 / v.rho * sqrt(c.A0 / A));
+  double u = q / A;
+  double a = fabs(u + w), b = fabs(u - w);
+  return 1.0 / (a > b ? a : b);
+}
+
+AF_HD double outlet_pressure(const Vessel& v, double A) {   // ar:285-301
+  return v.p0 + v.fL * (1.0 - sqrt(v.A0L / A));
+}
+
+// ---------------------------------------------------------------------------
+// Windkessel outlet (an:361-422)
+// ---------------------------------------------------------------------------
+struct WkResult {
+  double A_out, dex;
+  int its;
+};
+
+AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int Nx, double dt, double R1,
+                          double R2, double CT, int k_max, double tol, double margin) {
+  WkResult r;
+  double L = v.L;
+  Coef cL;
+  cL.f = v.fL; cL.A0 = v.A0L;
+  double AL, qL;
+  interp_state(A, q, Nx, v.dx, L, AL, qL);
+  double dex = (1.0 + margin) * dt / cfl_term(v, cL, AL, qL);       // adjust_dex (ar:349-365)
+  double x2 = L - 2.0 * dex, x1 = L - dex, x0 = L;
+  double x21 = L - 1.5 * dex, x10 = L - 0.5 * dex;
+  double A2, q2, A1, q1, A0s, q0s;
+  interp_state(A, q, Nx, v.dx, x2, A2, q2);
+  interp_state(A, q, Nx, v.dx, x1, A1, q1);
+  interp_state(A, q, Nx, v.dx, x0, A0s, q0s);
+  double Ah21, qh21, Ah10, qh10;
+  u_half(v, dt, x2, x1, A2, q2, A1, q1, Ah21, qh21);
+  u_half(v, dt, x1, x0, A1, q1, A0s, q0s, Ah10, qh10);
+  Coef c21 = coef_at(v, x21), c10 = coef_at(v, x10);
+  double F21 = bc_flux2(c21, Ah21, qh21), S21 = bc_source2(v, c21, Ah21, qh21);
+  double F10 = bc_flux2(c10, Ah10, qh10), S10 = bc_source2(v, c10, Ah10, qh10);
+  double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
+  double pn = outlet_pressure(v, A0s);
+  double p = pn;
+  double c_pn = dt / R1 / R2 / CT * pn;
+  double c_q = dt * (R1 + R2) / R1 / R2 / CT * q0s;
+  double dtdex = dt / dex;
+  double Am0 = A0s;
+  int k = 0;
+  for (; k < k_max;) {
+    double p_old = p;
+    double qm0 = q0s + (p - pn) / R1 + c_pn - c_q;
+    Am0 = A0s - dtdex * (qm0 - qm1);
+    p = outlet_pressure(v, Am0);
+    ++k;
+    if (fabs(p - p_old) < tol) break;
+  }
+  r.A_out = Am0;
+  r.dex = dex;
+  r.its = k;
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Bifurcation: 18 unknowns (an:476-710).  Unknown layout per vessel v
+// (0 = parent outlet, 1/2 = daughter inlets):
+//   x[3v] = q^{n+1}, x[3v+1] = q^{n+1/2}, x[3v+2] = q ghost^{n+1/2},
+//   x[9+3v], x[10+3v], x[11+3v] = the same for A.
+// ---------------------------------------------------------------------------
+struct JunctionCtx {
+  double dt;
+  double dtdex[3];      // dt/dex of each vessel
+  double Ae[3], qe[3];  // Un at the junction end
+  double Ah[3], qh[3];  // interior half-step state
+  double Fh2[3], Sh2[3];  // flux/source of it at the interior half point
+  Coef cg[3];           // Expressions at the ghost half point  L+dex/2 | -dex/2   (an:503-508)
+  Coef cj[3];           // Expressions at the Jacobian point    L+dex   | -dex     (an:589-597)
+  double fe[3], A0e[3];   // Expressions at the junction end
+  double src_k[3], rpi_dbRe[3];
+};
+
+// One vessel's share of the context.  `A`,`q` are that vessel's Un arrays.
+AF_HD void junction_prepare_vessel(JunctionCtx& c, int v, const Vessel& ves, const double* A, const double* q,
+                                   int Nx, double dt, double dex) {
+  double L = ves.L;
+  double xe = v == 0 ? L : 0.0;
+  double xi = v == 0 ? L - dex : dex;
+  double xg = v == 0 ? L + dex / 2.0 : -dex / 2.0;
+  double xh = v == 0 ? L - dex / 2.0 : dex / 2.0;
+  double xj = v == 0 ? L + dex : -dex;
+  double Ae, qe, Ai, qi;
+  interp_state(A, q, Nx, ves.dx, xe, Ae, qe);
+  interp_state(A, q, Nx, ves.dx, xi, Ai, qi);
+  double Ah, qh;
+  if (v == 0)
+    u_half(ves, dt, xi, xe, Ai, qi, Ae, qe, Ah, qh);
+  else
+    u_half(ves, dt, xe, xi, Ae, qe, Ai, qi, Ah, qh);
+  Coef ch = coef_at(ves, xh);
+  c.dt = dt;
+  c.dtdex[v] = dt / dex;
+  c.Ae[v] = Ae; c.qe[v] = qe;
+  c.Ah[v] = Ah; c.qh[v] = qh;
+  c.Fh2[v] = bc_flux2(ch, Ah, qh);
+  c.Sh2[v] = bc_source2(ves, ch, Ah, qh);
+  c.cg[v] = coef_at(ves, xg);
+  c.cj[v] = coef_at(ves, xj);
+  c.fe[v] = v == 0 ? ves.fL : ves.f0;
+  c.A0e[v] = v == 0 ? ves.A0L : ves.A00;
+  c.src_k[v] = ves.src_k;
+  c.rpi_dbRe[v] = ves.rpi_dbRe;
+}
+
+// problem_function (an:476-562)
+AF_HD void junction_residual(const JunctionCtx& c, const double* x, double* y) {
+  double ph[3], pf[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    double s = v == 0 ? 1.0 : -1.0;
+    double Ag = x[11 + 3 * v], qg = x[2 + 3 * v];
+    // ghost flux/source (an:503-508); only the Expression coefficients are
+    // needed from the Vessel, so the source is written out here
+    double Fg2 = qg * qg + c.cg[v].f * sqrt(c.cg[v].A0 * Ag);
+    double sA = sqrt(Ag);
+    double Sg2 = c.src_k[v] * qg / sA +
+                 (2.0 * sA * (kSqrtPi * c.cg[v].f + sqrt(c.cg[v].A0) * c.cg[v].dfdr) - Ag * c.cg[v].dfdr) *
+                     c.cg[v].drdx;
+    y[v] = 2.0 * x[3 * v + 1] - c.qh[v] - x[3 * v + 2];                       // eq (20)
+    y[3 + v] = 2.0 * x[10 + 3 * v] - c.Ah[v] - x[11 + 3 * v];                 // eq (21)
+    y[12 + v] = x[3 * v] - c.qe[v] + s * c.dtdex[v] * (Fg2 - c.Fh2[v]) - c.dt / 2.0 * (Sg2 + c.Sh2[v]);  // (26)
+    y[15 + v] = x[9 + 3 * v] - c.Ae[v] + s * c.dtdex[v] * (qg - c.qh[v]);     // eq (27)
+    ph[v] = c.fe[v] * (1.0 - sqrt(c.A0e[v] / x[10 + 3 * v]));
+    pf[v] = c.fe[v] * (1.0 - sqrt(c.A0e[v] / x[9 + 3 * v]));
+  }
+  y[6] = x[0] - x[3] - x[6];                                                  // eq (22)
+  y[7] = x[1] - x[4] - x[7];
+  y[8] = ph[0] - ph[1];                                                       // eq (23), p0 omitted
+  y[9] = ph[0] - ph[2];
+  y[10] = pf[0] - pf[1];
+  y[11] = pf[0] - pf[2];
+}
+
+// jacobian (an:565-665): hand-coded, 41 non-zeros, quirks kept.
+// J is row-major with leading dimension ld.
+AF_HD void junction_jacobian(const JunctionCtx& c, const double* x, double* J, int ld) {
+  for (int i = 0; i < 18; ++i)
+    for (int j = 0; j < 18; ++j) J[i * ld + j] = 0.0;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    double s = v == 0 ? 1.0 : -1.0;
+    int iq = 3 * v, iqh = 3 * v + 1, iqg = 3 * v + 2;
+    int iA = 9 + 3 * v, iAh = 10 + 3 * v, iAg = 11 + 3 * v;
+    J[v * ld + iqh] = 2.0;
+    J[v * ld + iqg] = -1.0;
+    J[(3 + v) * ld + iAh] = 2.0;
+    J[(3 + v) * ld + iAg] = -1.0;
+    double sg = v == 0 ? 1.0 : -1.0;
+    double k = c.fe[v] * sqrt(c.A0e[v]) / 2.0;
+    double dPh = sg * k / (x[iAh] * sqrt(x[iAh]));
+    double dPf = sg * k / (x[iA] * sqrt(x[iA]));
+    if (v == 0) {
+      J[8 * ld + iAh] = dPh;
+      J[9 * ld + iAh] = dPh;
+      J[10 * ld + iA] = dPf;
+      J[11 * ld + iA] = dPf;
+    } else {
+      J[(7 + v) * ld + iAh] = dPh;
+      J[(9 + v) * ld + iA] = dPf;
+    }
+    double qg = x[iqg], Ag = x[iAg];
+    double sA = sqrt(Ag);
+    const Coef& cj = c.cj[v];
+    J[(12 + v) * ld + iq] = 1.0;
+    J[(12 + v) * ld + iqg] = s * c.dtdex[v] * 2.0 * qg / Ag + c.dt * c.rpi_dbRe[v] / sA;
+    double u = qg / Ag;
+    J[(12 + v) * ld + iAg] =
+        s * c.dtdex[v] * (-(u * u) + cj.f / 2.0 * sqrt(cj.A0 / Ag)) -
+        c.dt / 2.0 * (c.rpi_dbRe[v] * qg / (Ag * sA) +
+                      (1.0 / sA * (kSqrtPi * cj.f + sqrt(cj.A0) * cj.dfdr) - cj.dfdr) * cj.drdx);
+    // row 17 uses d1's dt/dex (an:662)
+    J[(15 + v) * ld + iqg] = s * (v < 2 ? c.dtdex[v] : c.dtdex[1]);
+    J[(15 + v) * ld + iA] = 1.0;
+  }
+  J[6 * ld + 0] = 1.0; J[6 * ld + 3] = -1.0; J[6 * ld + 6] = -1.0;
+  J[7 * ld + 1] = 1.0; J[7 * ld + 4] = -1.0; J[7 * ld + 7] = -1.0;
+}
+
+// Dense LU with partial pivoting, the LAPACK dgesv recipe numpy.linalg.solve
+// runs (an:702).  Solves J dx = b in place (b <- dx).  Returns 1 if an exact
+// zero pivot is met (numpy raises LinAlgError there).
+AF_HD int lu_solve18(double* J, int ld, double* b) {
+  const int n = 18;
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = fabs(J[k * ld + k]);
+    for (int i = k + 1; i < n; ++i) {
+      double a = fabs(J[i * ld + k]);
+      if (a > best) { best = a; p = i; }
+    }
+    if (best == 0.0) return 1;
+    if (p != k) {
+      for (int j = 0; j < n; ++j) {
+        double t = J[k * ld + j]; J[k * ld + j] = J[p * ld + j]; J[p * ld + j] = t;
+      }
+      double t = b[k]; b[k] = b[p]; b[p] = t;
+    }
+    double inv = 1.0 / J[k * ld + k];
+    for (int i = k + 1; i < n; ++i) {
+      double l = J[i * ld + k] * inv;
+      if (l != 0.0) {
+        for (int j = k + 1; j < n; ++j) J[i * ld + j] -= l * J[k * ld + j];
+        b[i] -= l * b[k];
+      }
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < n; ++j) s -= J[i * ld + j] * b[j];
+    b[i] = s / J[i * ld + i];
+  }
+  return 0;
+}
+
+// newton (an:668-710).  Returns the number of linear solves; *flags gets
+// AF_FLAG_* bits.
+AF_HD int junction_newton(const JunctionCtx& c, double* x, int k_max, double tol, uint32_t* flags) {
+  double J[18 * 18], y[18];
+  int solves = 0;
+  int k = 0;
+  for (; k < k_max; ++k) {
+    junction_jacobian(c, x, J, 18);
+    junction_residual(c, x, y);
+    double nrm = 0.0;
+    for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
+    nrm = sqrt(nrm);
+    if (nrm < tol) break;
+    if (lu_solve18(J, 18, y)) {
+      // an:703-708: perturb and retry
+      *flags |= AF_FLAG_SINGULAR;
+      junction_jacobian(c, x, J, 18);
+      junction_residual(c, x, y);
+      for (int i = 0; i < 18; ++i) J[i * 18 + i] += 1.0e-6;
+      y[0] += 1.0e-6;
+      if (lu_solve18(J, 18, y)) break;
+    }
+    for (int i = 0; i < 18; ++i) x[i] -= y[i];
+    ++solves;
+  }
+  if (k == k_max) *flags |= AF_FLAG_JUNCTION_KMAX;
+  return solves;
+}
+
+// adjust_bifurcation_step (an:713-737): M of one vessel end
+AF_HD double junction_cfl(const Vessel& ves, int v, const double* A, const double* q, int Nx) {
+  Coef ce;
+  ce.f = v == 0 ? ves.fL : ves.f0;
+  ce.A0 = v == 0 ? ves.A0L : ves.A00;
+  double Ae, qe;
+  interp_state(A, q, Nx, ves.dx, v == 0 ? ves.L : 0.0, Ae, qe);
+  return cfl_term(ves, ce, Ae, qe);
+}
+
+// ---------------------------------------------------------------------------
+// Per-artery theta-scheme weak form (ar:191-230) + [3P] assembly, one cell.
+// ---------------------------------------------------------------------------
+struct ArteryConst {
+  double h, dt, theta;
+  double Kr;            // 2*sqrt(pi)/(db*Re)
+};
+
+// Coefficients at the three Gauss points of one cell, derived from the P2
+// interpolants f_h, A0_h, dfdr_h, drdx_h ([3P]):
+//   c1 = f_h*sqrt(A0_h), t2 = (sqrt(pi) f_h + sqrt(A0_h) dfdr_h) drdx_h, t3 = dfdr_h*drdx_h
+struct CellCoef {
+  double c1[3], t2[3], t3[3];
+};
+
+AF_HD void p2_to_gauss(double vl, double vr, double vm, double out[3]) {
+  const double xi[3] = {kXi0, kXi1, kXi2};
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    double n0 = (1.0 - xi[g]) * (1.0 - 2.0 * xi[g]);
+    double n1 = xi[g] * (2.0 * xi[g] - 1.0);
+    double nm = 4.0 * xi[g] * (1.0 - xi[g]);
+    out[g] = vl * n0 + vr * n1 + vm * nm;
+  }
+}
+
+AF_HD CellCoef cell_coef(const Vessel& v, double xl, double xr) {
+  Coef cl = coef_at(v, xl), cr = coef_at(v, xr), cm = coef_at(v, 0.5 * (xl + xr));
+  double f[3], A0[3], df[3], dr[3];
+  p2_to_gauss(cl.f, cr.f, cm.f, f);
+  p2_to_gauss(cl.A0, cr.A0, cm.A0, A0);
+  p2_to_gauss(cl.dfdr, cr.dfdr, cm.dfdr, df);
+  p2_to_gauss(cl.drdx, cr.drdx, cm.drdx, dr);
+  CellCoef c;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    double sA0 = sqrt(A0[g]);
+    c.c1[g] = f[g] * sA0;
+    c.t2[g] = (kSqrtPi * f[g] + sA0 * df[g]) * dr[g];
+    c.t3[g] = df[g] * dr[g];
+  }
+  return c;
+}
+
+// F2 = q^2/A + f sqrt(A0 A), S2 (ar:197-222) and their derivatives at one point
+struct PointTerms {
+  double F2, S2, dF2dA, dF2dq, dS2dA, dS2dq;
+};
+
+template <bool JAC>
+AF_HD PointTerms point_terms(double A, double q, double c1, double t2, double t3, double Kr) {
+  PointTerms t;
+  double inv = 1.0 / A;
+  double sA = sqrt(A);
+  double isA = sA * inv;
+  double qi = q * inv;
+  t.F2 = q * qi + c1 * sA;
+  t.S2 = -Kr * q * isA + 2.0 * sA * t2 - A * t3;
+  if (JAC) {
+    t.dF2dA = -qi * qi + 0.5 * c1 * isA;
+    t.dF2dq = 2.0 * qi;
+    t.dS2dA = 0.5 * Kr * qi * isA + t2 * isA - t3;
+    t.dS2dq = -Kr * isA;
+  }
+  return t;
+}
+
+// One cell's contribution.  rl/rr: residual rows (A, q) of its left/right
+// vertex.  b00..b11: 2x2 blocks (row-major: [A-row A-col, A-row q-col, q-row
+// A-col, q-row q-col]) d R[(i)] / d U[(j)], i, j in {left, right}.
+template <bool JAC>
+AF_HD void cell_assemble(const ArteryConst& ac, const CellCoef& cc, double Al, double Ar, double ql, double qr,
+                         double Anl, double Anr, double qnl, double qnr, double rl[2], double rr[2],
+                         double b00[4], double b01[4], double b10[4], double b11[4]) {
+  const double xi[3] = {kXi0, kXi1, kXi2};
+  const double wq[3] = {kW0, kW1, kW2};
+  const double h = ac.h, dt = ac.dt, th = ac.theta, om = 1.0 - ac.theta;
+  const double dphi0 = -1.0 / h, dphi1 = 1.0 / h;
+  double qx = (qr - ql) / h, qnx = (qnr - qnl) / h;
+  double dq_mix = dt * (th * qx + om * qnx);
+  rl[0] = rl[1] = rr[0] = rr[1] = 0.0;
+  if (JAC) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b00[k] = b01[k] = b10[k] = b11[k] = 0.0;
+  }
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    double p0 = 1.0 - xi[g], p1 = xi[g];
+    double w = wq[g] * h;
+    double A = Al * p0 + Ar * p1, q = ql * p0 + qr * p1;
+    double An = Anl * p0 + Anr * p1, qn = qnl * p0 + qnr * p1;
+    PointTerms tn = point_terms<false>(An, qn, cc.c1[g], cc.t2[g], cc.t3[g], ac.Kr);
+    PointTerms t = point_terms<JAC>(A + kDolfinEps, q, cc.c1[g], cc.t2[g], cc.t3[g], ac.Kr);
+    double Fm = dt * (th * t.F2 + om * tn.F2);
+    double Sm = dt * (th * t.S2 + om * tn.S2);
+    double ra = (A - An) + dq_mix;
+    double dq = q - qn;
+    rl[0] += w * (ra * p0);
+    rr[0] += w * (ra * p1);
+    rl[1] += w * (dq * p0 - Fm * dphi0 - Sm * p0);
+    rr[1] += w * (dq * p1 - Fm * dphi1 - Sm * p1);
+    if (JAC) {
+      double dth = dt * th;
+      // rows of vertex i, columns of vertex j
+      const double pi_[2] = {p0, p1}, dpi_[2] = {dphi0, dphi1};
+      double* blk[2][2] = {{b00, b01}, {b10, b11}};
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          double* b = blk[i][j];
+          double pp = pi_[i] * pi_[j];
+          b[0] += w * pp;
+          b[1] += w * (dth * dpi_[j] * pi_[i]);
+          b[2] -= w * (dth * (t.dF2dA * pi_[j] * dpi_[i] + t.dS2dA * pp));
+          b[3] += w * (pp - dth * (t.dF2dq * pi_[j] * dpi_[i] + t.dS2dq * pp));
+        }
+    }
+  }
+}
+
+// Exterior-facet term "+F2*v2*ds" on the q row of an end vertex (ar:197-198,
+// 206-207; no outward normal).  c1v = f(x_v)*sqrt(A0(x_v)).
+template <bool JAC>
+AF_HD void facet_term(const ArteryConst& ac, double c1v, double A, double q, double An, double qn, double& rq,
+                      double& dA, double& dq) {
+  PointTerms tn = point_terms<false>(An, qn, c1v, 0.0, 0.0, 0.0);
+  PointTerms t = point_terms<JAC>(A + kDolfinEps, q, c1v, 0.0, 0.0, 0.0);
+  rq = ac.dt * (ac.theta * t.F2 + (1.0 - ac.theta) * tn.F2);
+  if (JAC) {
+    dA = ac.dt * ac.theta * t.dF2dA;
+    dq = ac.dt * ac.theta * t.dF2dq;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 2x2-block tridiagonal solve by in-place block cyclic reduction.
+// Arrays are component-major: blk[c*ld + i], c = 0..3 (row-major 2x2), rhs[c*ld + i].
+// ---------------------------------------------------------------------------
+AF_HD void inv2(const double* m, int ld, int i, double o[4]) {
+  double a = m[i], b = m[ld + i], c = m[2 * ld + i], d = m[3 * ld + i];
+  double r = 1.0 / (a * d - b * c);
+  o[0] = d * r; o[1] = -b * r; o[2] = -c * r; o[3] = a * r;
+}
+
+AF_HD void ld2(const double* m, int ld, int i, double o[4]) {
+  o[0] = m[i]; o[1] = m[ld + i]; o[2] = m[2 * ld + i]; o[3] = m[3 * ld + i];
+}
+
+AF_HD void mul2(const double a[4], const double b[4], double o[4]) {
+  o[0] = a[0] * b[0] + a[1] * b[2];
+  o[1] = a[0] * b[1] + a[1] * b[3];
+  o[2] = a[2] * b[0] + a[3] * b[2];
+  o[3] = a[2] * b[1] + a[3] * b[3];
+}
+
+// forward step of level s for node i ((i+1) % 2s == 0): eliminate i-s and i+s
+AF_HD void cr_forward(int i, int s, int n, double* Lo, double* Dg, double* Up, double* R, int ld) {
+  double d[4], r0, r1, lo[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
+  ld2(Dg, ld, i, d);
+  r0 = R[i]; r1 = R[ld + i];
+  {
+    int j = i - s;   // always >= 0
+    double inv[4], l[4], al[4], t[4];
+    inv2(Dg, ld, j, inv);
+    ld2(Lo, ld, i, l);
+    mul2(l, inv, al);                 // al = Lo_i * D_j^-1
+    ld2(Up, ld, j, t);
+    double m[4];
+    mul2(al, t, m);
+    d[0] -= m[0]; d[1] -= m[1]; d[2] -= m[2]; d[3] -= m[3];
+    r0 -= al[0] * R[j] + al[1] * R[ld + j];
+    r1 -= al[2] * R[j] + al[3] * R[ld + j];
+    ld2(Lo, ld, j, t);
+    mul2(al, t, m);
+    lo[0] = -m[0]; lo[1] = -m[1]; lo[2] = -m[2]; lo[3] = -m[3];
+  }
+  int j = i + s;
+  if (j < n) {
+    double inv[4], u[4], ga[4], t[4], m[4];
+    inv2(Dg, ld, j, inv);
+    ld2(Up, ld, i, u);
+    mul2(u, inv, ga);                 // ga = Up_i * D_j^-1
+    ld2(Lo, ld, j, t);
+    mul2(ga, t, m);
+    d[0] -= m[0]; d[1] -= m[1]; d[2] -= m[2]; d[3] -= m[3];
+    r0 -= ga[0] * R[j] + ga[1] * R[ld + j];
+    r1 -= ga[2] * R[j] + ga[3] * R[ld + j];
+    ld2(Up, ld, j, t);
+    mul2(ga, t, m);
+    up[0] = -m[0]; up[1] = -m[1]; up[2] = -m[2]; up[3] = -m[3];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    Dg[c * ld + i] = d[c];
+    Lo[c * ld + i] = lo[c];
+    Up[c * ld + i] = up[c];
+  }
+  R[i] = r0; R[ld + i] = r1;
+}
+
+// back-substitution of level s for node i ((i+1) % 2s == s): neighbours i-s, i+s are known.
+// The solution overwrites R.
+AF_HD void cr_backward(int i, int s, int n, const double* Lo, const double* Dg, const double* Up, double* R,
+                       int ld) {
+  double r0 = R[i], r1 = R[ld + i];
+  int j = i - s;
+  if (j >= 0) {
+    double l[4];
+    ld2(Lo, ld, i, l);
+    r0 -= l[0] * R[j] + l[1] * R[ld + j];
+    r1 -= l[2] * R[j] + l[3] * R[ld + j];
+  }
+  j = i + s;
+  if (j < n) {
+    double u[4];
+    ld2(Up, ld, i, u);
+    r0 -= u[0] * R[j] + u[1] * R[ld + j];
+    r1 -= u[2] * R[j] + u[3] * R[ld + j];
+  }
+  double inv[4];
+  inv2(Dg, ld, i, inv);
+  R[i] = inv[0] * r0 + inv[1] * r1;
+  R[ld + i] = inv[2] * r0 + inv[3] * r1;
+}
+
+}  // namespace af

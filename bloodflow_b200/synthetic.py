@@ -1,0 +1,64 @@
+"""Synthetic symmetric trees and UQ ensembles of the shapes BASELINE.json names
+(SURVEY.md 8(d) recipe).  Produces objects with the ``.param/.geo/.solution``
+dicts of a ParamParser, i.e. exactly what a .cfg file of the reference would
+hold, so they go through the same ArteryNetwork constructor.
+
+Recipe: ``build_geometry`` tree with alpha, L; untapered leaves
+(R_term = Ru0*alpha**(order-1)); per leaf R_tot = p0/(mean_flow/n_leaves),
+R1_eff = 2*Z0 (Picard gain 0.5), R2_eff = R_tot - R1_eff, CT = tau/R2_eff; the
+cfg values are divided by HEAD's factors 0.3 / 0.01 so HEAD lands on them.
+"""
+import os
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INLET = os.path.join(ROOT, 'data', 'example_inlet.csv')
+
+PHYS = dict(rc=1.0, qc=10.0, k1=2.0e7, k2=-22.53, k3=8.65e5, rho=1.06, nu=0.046, p0=119990.131579)
+
+
+def leaf_windkessel(order, Ru0=0.37, alpha=0.8, mean_flow=5.5, tau=0.0186, phys=PHYS):
+    """(R1, R2, CT) cfg values (dimensional, before HEAD's factors) of one leaf."""
+    r = Ru0 * alpha ** (order - 1)
+    n_leaves = 2 ** (order - 1)
+    f = 4.0 / 3.0 * (phys['k1'] * np.exp(phys['k2'] * r) + phys['k3'])
+    Z0 = phys['rho'] * np.sqrt(f / (2 * phys['rho'])) / (np.pi * r * r)
+    R_tot = phys['p0'] / (mean_flow / n_leaves)
+    R1_eff = 2 * Z0
+    R2_eff = R_tot - R1_eff
+    return R1_eff / 0.3, R2_eff / 0.01, tau / R2_eff
+
+
+def tree_param(order, Nx, Nt, N_cycles=1, Nt_store=None, N_cycles_store=1, Ru0=0.37, alpha=0.8, L=20.0,
+               theta=0.55, output_location='output/synthetic', inlet=INLET, store_area=1, store_pressure=1):
+    """ParamParser-like description of a symmetric tree of ``order`` levels."""
+    N = 2 ** order - 1
+    n_leaves = 2 ** (order - 1)
+    R1, R2, CT = leaf_windkessel(order, Ru0, alpha)
+    mult = np.ones(N)
+    mult[0] = Ru0
+    param = dict(PHYS)
+    param.update(order=order, Ru=mult.copy(), Rd=mult.copy(), alpha=alpha, L=L,
+                 R_term=Ru0 * alpha ** (order - 1), p_term=6000.0,
+                 R1=np.full(n_leaves, R1), R2=np.full(n_leaves, R2), CT=np.full(n_leaves, CT))
+    geo = dict(Nx=Nx, Nt=Nt, N_cycles=N_cycles)
+    sol = dict(inlet_flow_location=inlet, output_location=output_location, theta=theta,
+               Nt_store=Nt_store if Nt_store is not None else min(Nt, 100), N_cycles_store=N_cycles_store,
+               store_area=store_area, store_pressure=store_pressure)
+    return types.SimpleNamespace(param=param, geo=geo, solution=sol, fparams=None)
+
+
+def write_cfg(p, path):
+    """Write a tree_param() description as a reference-format .cfg file."""
+    def fmt(v):
+        if np.ndim(v):
+            return ','.join(repr(float(x)) for x in v)
+        return repr(v) if not isinstance(v, str) else v
+    with open(path, 'w') as fh:
+        for section, d in (('Parameters', p.param), ('Geometry', p.geo), ('Solution', p.solution)):
+            fh.write('[%s]\n' % section)
+            for k, v in d.items():
+                fh.write('%s = %s\n' % (k, fmt(v)))
+            fh.write('\n')

@@ -1,0 +1,166 @@
+"""The kernels' per-thread FP64 math (bloodflow_b200/csrc/af_physics.cuh),
+compiled for the host by tests/host_harness, against the oracle.  Lets the
+formulas be checked in the CPU-only container; the device run of the same code
+is covered by the -m gpu tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from oracle import arteryfe_oracle as ao
+
+HH_DIR = os.path.join(ROOT, 'tests', 'host_harness')
+c_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+@pytest.fixture(scope='module')
+def hh():
+    so = os.path.join(HH_DIR, 'libaf_host_harness.so')
+    src = os.path.join(HH_DIR, 'harness.cpp')
+    hdr = os.path.join(ROOT, 'bloodflow_b200', 'csrc', 'af_physics.cuh')
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC',
+                               '-x', 'c++', src, '-o', so])
+    lib = ctypes.CDLL(so)
+    lib.hh_junction_cfl_dex.restype = ctypes.c_double
+    lib.hh_junction_cfl_dex.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, ctypes.c_double]
+    lib.hh_junction_eval.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp, c_dp, c_dp]
+    lib.hh_junction_newton.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp, ctypes.c_int,
+                                       ctypes.c_double, ctypes.POINTER(ctypes.c_uint)]
+    lib.hh_windkessel.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_dp]
+    lib.hh_artery_solve.argtypes = [c_dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_dp, c_dp, c_dp,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                    c_dp, c_dp, c_dp]
+    lib.hh_coef.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, c_dp, c_dp]
+    lib.hh_interp.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_int, c_dp, c_dp]
+    return lib
+
+
+def vessel_params(a):
+    p = a.param
+    return np.array([a.Ru, a.Rd, a.L, a.k1, a.k2, a.k3, p['rho'], p['Re'], a.db, p['p0']], dtype=float)
+
+
+def load_state(case, step):
+    g = np.load(os.path.join(GOLDEN, 'bc_%s.npz' % case))
+    net = ao.network_from_cfg(os.path.join(GOLDEN, 'golden_%s.cfg' % case))
+    arts = [a for a in net.arteries if a is not None]
+    for a, Un in zip(arts, g['s%d_Un' % step]):
+        a._Un[:] = Un
+        a._U[:] = Un
+    net.x[:] = g['s%d_x_in' % step]
+    return net, g
+
+
+CASES = [('c1', 0), ('c1', 25), ('c2', 3), ('o3', 25)]
+
+
+@pytest.mark.parametrize('case,step', CASES)
+def test_expressions_and_interpolation(hh, case, step):
+    net, _ = load_state(case, step)
+    for a in net.arteries:
+        vp = vessel_params(a)
+        x = np.array([-0.3, 0.0, 0.123 * a.L, 0.5 * a.L, a.L - 1e-9, a.L, a.L + 0.4])
+        out = np.zeros((len(x), 4))
+        hh.hh_coef(_dp(vp), a.Nx, len(x), _dp(x), _dp(out))
+        want = np.array([[a.f(s), a.A0(s), a.dfdr(s), a.drdx(s)] for s in x])
+        np.testing.assert_allclose(out, want, rtol=1e-14, atol=1e-18)
+        xs = np.array([0.0, 0.37 * a.L, a.L - 2.2 * a.dx, a.L])
+        A, q = np.ascontiguousarray(a._Un[:, 0]), np.ascontiguousarray(a._Un[:, 1])
+        o2 = np.zeros((len(xs), 2))
+        hh.hh_interp(_dp(vp), a.Nx, _dp(A), _dp(q), len(xs), _dp(xs), _dp(o2))
+        np.testing.assert_allclose(o2, [a.Un(s) for s in xs], rtol=1e-14)
+
+
+@pytest.mark.parametrize('case,step', CASES)
+def test_junction_math(hh, case, step):
+    net, _ = load_state(case, step)
+    for k, ip in enumerate(net.range_parent_arteries):
+        i1, i2 = net.daughter_arteries(ip)
+        ves = [net.arteries[i] for i in (ip, i1, i2)]
+        vp = np.concatenate([vessel_params(a) for a in ves])
+        A = np.ascontiguousarray(np.array([a._Un[:, 0] for a in ves]))
+        q = np.ascontiguousarray(np.array([a._Un[:, 1] for a in ves]))
+        Nx = ves[0].Nx
+        net.adjust_bifurcation_step(*ves)
+        dex = hh.hh_junction_cfl_dex(_dp(vp), Nx, _dp(A), _dp(q), net.dt, 0.05)
+        np.testing.assert_allclose(dex, ves[0].dex, rtol=1e-14)
+        dex3 = np.full(3, ves[0].dex)
+        x = net.x[k].copy()
+        y, J = np.zeros(18), np.zeros((18, 18))
+        hh.hh_junction_eval(_dp(vp), Nx, _dp(A), _dp(q), net.dt, _dp(dex3), _dp(x), _dp(y), _dp(J))
+        np.testing.assert_allclose(y, net.problem_function(*ves, x), rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(J, net.jacobian(*ves, x), rtol=1e-13, atol=0)
+        # distinct dex per vessel (the facade allows it) and a perturbed x
+        dexv = dex3 * np.array([1.0, 1.07, 0.93])
+        for a, d in zip(ves, dexv):
+            a.dex = d
+        xp = x * (1 + 0.01 * np.sin(np.arange(18)))
+        hh.hh_junction_eval(_dp(vp), Nx, _dp(A), _dp(q), net.dt, _dp(dexv), _dp(xp), _dp(y), _dp(J))
+        np.testing.assert_allclose(y, net.problem_function(*ves, xp), rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(J, net.jacobian(*ves, xp), rtol=1e-13, atol=0)
+        for a in ves:
+            a.dex = dex3[0]
+        xs = x.copy()
+        fl = ctypes.c_uint(0)
+        solves = hh.hh_junction_newton(_dp(vp), Nx, _dp(A), _dp(q), net.dt, _dp(dex3), _dp(xs), 30, 1e-10,
+                                       ctypes.byref(fl))
+        want = net.newton(*ves, x.copy())
+        assert solves == net._last_junction_solves
+        assert fl.value == 0
+        np.testing.assert_allclose(xs, want, rtol=1e-11)
+
+
+@pytest.mark.parametrize('case,step', CASES)
+def test_windkessel_math(hh, case, step):
+    net, _ = load_state(case, step)
+    for i in net.range_leaf_arteries:
+        a = net.arteries[i]
+        A, q = np.ascontiguousarray(a._Un[:, 0]), np.ascontiguousarray(a._Un[:, 1])
+        out = np.zeros(3)
+        hh.hh_windkessel(_dp(vessel_params(a)), a.Nx, _dp(A), _dp(q), net.dt, a.param['R1'] * 0.3,
+                         a.param['R2'] * 0.01, a.param['CT'], 100, 1e-12, 0.05, _dp(out))
+        want = net.windkessel(a)
+        np.testing.assert_allclose(out[0], want, rtol=1e-13)
+        np.testing.assert_allclose(out[1], a.dex, rtol=1e-14)
+        # the Picard map stagnates within a few ulp of p; the count may differ by round-off
+        assert out[2] == net._last_picard_its or min(out[2], net._last_picard_its) > 15
+
+
+@pytest.mark.parametrize('case,step', CASES)
+def test_artery_assembly_and_newton(hh, case, step):
+    net, _ = load_state(case, step)
+    net.set_bcs(net.q_ins[(step + 1) % net.geo['Nt']])
+    for a in net.arteries:
+        np_ = a.Nx + 1
+        bc = np.zeros(4)
+        if a.root:
+            bc[1] = a.q_in
+        else:
+            bc[:2] = a.U_in
+        if a.leaf:
+            bc[2] = a.A_out
+        else:
+            bc[2:] = a.U_out
+        A, q = np.ascontiguousarray(a._Un[:, 0]), np.ascontiguousarray(a._Un[:, 1])
+        R, J = np.zeros((np_, 2)), np.zeros((3, np_, 2, 2))
+        r_last = ctypes.c_double(0)
+        its = hh.hh_artery_solve(_dp(vessel_params(a)), a.Nx, a.dt, a.theta, _dp(A), _dp(q), _dp(bc),
+                                 int(a.root), int(a.leaf), 1e-9, 1e-10, 1000, ctypes.byref(r_last), _dp(R), _dp(J))
+        Rw, (Lo, Dg, Up) = a.assemble(a._U, jacobian=True)
+        scale = np.abs(Rw).max()
+        np.testing.assert_allclose(R, Rw, rtol=0, atol=1e-13 * max(scale, 1.0))
+        for got, want in zip(J, (Lo, Dg, Up)):
+            np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13 * np.abs(Dg).max())
+        a.solve()
+        assert its == a.newton_its
+        np.testing.assert_allclose(A, a._U[:, 0], rtol=1e-11)
+        np.testing.assert_allclose(q, a._U[:, 1], rtol=1e-10, atol=1e-12)
