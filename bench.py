@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- artery-node-timesteps/s of the per-timestep network solve.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json config 4, the one the 1e9 target is quoted on): the
+synthetic order-8 tree, 255 arteries x 1001 vertices, Nt = 8000 steps per
+cardiac cycle, Windkessel outlets on the 128 leaves, data/example_inlet.csv.
+A "step" is one time step of the whole network (set_bcs + every artery solve).
+
+N GPUs: an ensemble of N parameter-perturbed order-8 trees (member 0 is the
+nominal tree), one per GPU -- the path shards over independent networks only
+(DESIGN.md "Multi-GPU"); weak scaling.  The only collective is the NCCL
+all-reduce of the outlet-pressure moments after the timed loop.
+
+One JSON line on stdout (rank 0).  `value` is timed with CUDA events on the
+stream the kernels run on, inputs resident in HBM; `e2e` is the same metric
+through the public arteryfe API (ArteryNetwork(param).solve()) with host
+buffers: upload of the network description, the loop with its snapshots,
+download of the snapshots.
+
+--impl reference: the reference CPU path.  FEniCS cannot run here, so this is
+the C restatement oracle/oracle.c ("restated reference"), OpenMP over all host
+cores, same config and metric.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.chdir(ROOT)
+
+METRIC = "artery-node-timesteps/sec"
+UNIT = "node-steps/s"
+ORDER, NX, NT = 8, 1000, 8000
+NT_STORE = 100
+
+
+def ensemble_member(order, Nx, Nt, member, N_cycles=4):
+    """Member `member` of the UQ ensemble around the nominal tree: stiffness
+    (k1, k3 common factor), root radius, per-leaf R1, R2, CT sampled as in
+    SURVEY 8(d) C5; member 0 is the nominal network."""
+    from bloodflow_b200.synthetic import tree_param
+    p = tree_param(order, Nx=Nx, Nt=Nt, N_cycles=N_cycles, Nt_store=NT_STORE)
+    if member:
+        rng = np.random.Generator(np.random.PCG64(20260000 + member))
+        s = rng.uniform(0.9, 1.1)
+        p.param['k1'] *= s
+        p.param['k3'] *= s
+        r = rng.uniform(0.9, 1.1)
+        p.param['Ru'][0] *= r
+        p.param['Rd'][0] *= r
+        p.param['R_term'] *= r
+        n_l = len(p.param['R1'])
+        p.param['R1'] = p.param['R1'] * rng.uniform(0.8, 1.2, n_l)
+        p.param['R2'] = p.param['R2'] * rng.uniform(0.8, 1.2, n_l)
+        p.param['CT'] = p.param['CT'] * rng.uniform(0.8, 1.2, n_l)
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_baseline(order, Nx, Nt, budget_s=12.0):
+    """C oracle on all host cores over a bounded sample of the same workload."""
+    from oracle import arteryfe_oracle as ao
+    from oracle.oracle_c import COracle
+    p = ensemble_member(order, Nx, Nt, 0)
+    net = ao.OracleNetwork(p.param, p.geo, p.solution)
+    c = COracle(net)
+    cores = os.cpu_count() or 1
+    nodes = c.na * c.np
+    t0 = time.perf_counter()
+    c.step(0, 4, nthreads=cores)
+    per = (time.perf_counter() - t0) / 4
+    n = int(max(8, min(4000, budget_s / per)))
+    t0 = time.perf_counter()
+    failed = c.step(4, n, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": nodes * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d time steps of the same order-%d tree after 4 warm-up steps, oracle/oracle.c with "
+                      "OpenMP over arteries/junctions (%s)" % (n, order, "ok" if not failed else "FAILED"),
+            "ms_per_step": dt / n * 1e3}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import arteryfe_oracle as ao
+    from oracle.oracle_c import COracle
+    p = ensemble_member(args.order, args.Nx, args.Nt, 0)
+    net = ao.OracleNetwork(p.param, p.geo, p.solution)
+    c = COracle(net)
+    cores = os.cpu_count() or 1
+    nodes = c.na * c.np
+    W, K = args.warmup, args.steps
+    t0 = time.perf_counter()
+    c.step(0, W, nthreads=cores)
+    per = (time.perf_counter() - t0) / max(W, 1)
+    K_run = K
+    if per * K > 150.0:                      # keep the run within a few minutes
+        K_run = max(10, int(150.0 / per))
+    t0 = time.perf_counter()
+    failed = c.step(W, K_run, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = nodes * K_run / dt
+    sample = ("%d of the requested %d time steps of the order-%d tree (bounded sample), oracle/oracle.c, "
+              "OpenMP %d threads" % (K_run, K, args.order, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": K_run, "warmup": W, "ms_per_step": dt / K_run * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference CPU path = C restatement of the reference scheme (FEniCS 2017.2.0 cannot be "
+                "installed here); failed=%d" % failed,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "synthetic symmetric tree order=%d (%d arteries x %d vertices), Nt=%d per cycle, "
+                        "Windkessel outlets on %d leaves, data/example_inlet.csv; N GPUs = N perturbed "
+                        "members, one per GPU" % (args.order, 2 ** args.order - 1, args.Nx + 1, args.Nt,
+                                                  2 ** (args.order - 1)),
+            "order": args.order, "Nx": args.Nx, "Nt": args.Nt, "theta": 0.55,
+            "l2": "no flush: the time loop is a dependent chain (step n+1 reads exactly what step n wrote), so "
+                  "L2 residency of the %.1f MB state is the real operating point; nothing is cached or skipped "
+                  "across timed steps" % ((2 ** args.order - 1) * (args.Nx + 1) * 32 / 1e6),
+            "parallelism": "ensemble-dp%d" % args.gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--order', type=int, default=ORDER)
+    ap.add_argument('--Nx', type=int, default=NX)
+    ap.add_argument('--Nt', type=int, default=NT)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the "
+                         "CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    import bloodflow_b200.arteryfe as af
+    from bloodflow_b200 import _ffi
+    from bloodflow_b200.engine import DeviceNetwork
+
+    K, W = args.steps, max(args.warmup, 3)
+    p = ensemble_member(args.order, args.Nx, args.Nt, rank)
+    # the library enqueues on a torch stream, so torch CUDA events time exactly its kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    an = af.ArteryNetwork(p, device=local_rank, stream=stream.cuda_stream)
+    dev = an._dev
+    nodes = dev.na * dev.np
+    an.define_x()
+    mask = an.store_mask()
+    dev.set_store(mask, 0, max(1, (K + W) // (args.Nt // NT_STORE) + 2), _ffi.AF_STORE_OUTLET_PRESSURE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed loop: W warm-up steps, then exactly K steps ----------
+    dev.step(0, W)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    dev.step(W, K)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * nodes * K / (ms_total * 1e-3)
+    phase = phase_times(dev, stream, W + K, args.Nt, torch)
+
+    # ---- ensemble statistics: the one collective of the path ---------------------------
+    snaps = dev.fetch_snapshots()
+    op = torch.as_tensor(snaps['outlet_pressure'][:, 0, :], device='cuda')
+    stats = torch.stack([op, op * op, op, op], dim=0)
+    coll_ms = None
+    if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(stats[0], op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats[1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats[2], op=dist.ReduceOp.MIN)
+        dist.all_reduce(stats[3], op=dist.ReduceOp.MAX)
+        e1.record()
+        torch.cuda.synchronize()
+        coll_ms = e0.elapsed_time(e1)
+    mean_p = (stats[0] / world).mean().item()
+
+    flags = int(dev.get_flags()[0])
+    totals = dev.get_totals()
+
+    # ---- end to end through the public API (rank-local, then max over ranks) -----------
+    e2e = end_to_end(args, rank, local_rank, K, nodes)
+    te = torch.tensor([e2e['seconds']], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * nodes * K / float(te.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fp64_peak = ctypes_fp64_peak(local_rank)
+        art_us = phase['artery_us']
+        bytes_per_launch = nodes * 32.0
+        achieved = bytes_per_launch / (art_us * 1e-6) / 1e9
+        its_per_step = totals[0] / float(dev.na * (K + W))
+        flops_per_node_step = (its_per_step + 1) * 110 + its_per_step * (140 + 50)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "cycles_per_sec_per_network": 1.0 / (ms_total * 1e-3 / K * args.Nt),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "kernel": "k_artery", "kernel_us": art_us, "kernel_share_of_step": phase['artery_share'],
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "note": "32 B per vertex-step (read A,q; write A,q), untapered tree streams no coefficients; "
+                        "the kernel is latency/FP64-bound, not HBM-bound (DESIGN.md)",
+                "fp64": {"achieved_tflops": flops_per_node_step * nodes / (art_us * 1e-6) / 1e12,
+                         "peak_tflops": fp64_peak, "flops_per_vertex_step": flops_per_node_step,
+                         "newton_its_per_artery_step": its_per_step},
+            },
+            "phases_us": phase,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e['h2d'] / K,
+                    "d2h_bytes_per_step": e2e['d2h'] / K, "seconds": float(te.item()),
+                    "api": "arteryfe.ArteryNetwork(param).solve(n_steps=K): create+upload, loop with %d-step "
+                           "snapshot cadence, fetch of flow/area/pressure snapshots" % (args.Nt // NT_STORE)},
+            "gpu_launches": 2 * K + int(np.sum(np.tile(mask, 1 + (W + K) // args.Nt)[W:W + K])),
+            "clocks": clocks, "wall_seconds_host": wall,
+            "status": {"flags": flags, "artery_solves": int(totals[0]), "junction_solves": int(totals[1]),
+                       "picard_its": int(totals[2]), "mean_outlet_pressure": mean_p,
+                       "collective_ms": coll_ms},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.order, args.Nx, args.Nt)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctypes_fp64_peak(device):
+    import ctypes
+    from bloodflow_b200 import _ffi
+    v = ctypes.c_double(0)
+    _ffi.check(_ffi.lib.af_measure_fp64_peak(device, ctypes.byref(v)))
+    return v.value
+
+
+def phase_times(dev, stream, g0, Nt, torch, n=200):
+    """Average duration of the two kernels of a step (boundary / artery), CUDA
+    events on the launching stream, over n further steps of the same run."""
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    for i in range(n):
+        g = g0 + i
+        evs[i][0].record(stream)
+        dev.phase_boundary()
+        evs[i][1].record(stream)
+        dev.phase_arteries((g % Nt + 1) % Nt)
+        evs[i][2].record(stream)
+    dev.sync()
+    b = np.array([e[0].elapsed_time(e[1]) for e in evs]) * 1e3
+    a = np.array([e[1].elapsed_time(e[2]) for e in evs]) * 1e3
+    return {"boundary_us": float(np.mean(b)), "artery_us": float(np.mean(a)),
+            "artery_share": float(np.mean(a) / (np.mean(a) + np.mean(b))), "sampled_steps": n}
+
+
+def end_to_end(args, rank, local_rank, K, nodes):
+    import bloodflow_b200.arteryfe as af
+    n_cycles = -(-K // args.Nt)
+    p = ensemble_member(args.order, args.Nx, args.Nt, rank, N_cycles=n_cycles)
+    p.solution['N_cycles_store'] = n_cycles          # snapshots from the first step on
+    t0 = time.perf_counter()
+    an = af.ArteryNetwork(p, device=local_rank)
+    res = an.solve(write_output=False, n_steps=K)
+    dt = time.perf_counter() - t0
+    d2h = sum(res[k].nbytes for k in ('flow', 'area', 'pressure') if k in res)
+    h2d = an.q_ins.nbytes + an._dev.na * 4 * 8 + an._dev.nl * 3 * 8 + 7 * 8 + (an._dev.nj * 3 + an._dev.nl) * 4
+    return {"seconds": dt, "h2d": h2d, "d2h": d2h, "flags": an.flags}
+
+
+if __name__ == '__main__':
+    main()

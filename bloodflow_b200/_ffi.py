@@ -83,6 +83,7 @@ PROTOTYPES = {
     'af_junction_eval': (c_int, [Handle, c_i32, c_i32, P_dbl, P_dbl, P_dbl, P_dbl]),
     'af_junction_newton': (c_int, [Handle, c_i32, c_i32, P_dbl, P_dbl, c_i32, c_dbl, P_i32]),
     'af_windkessel': (c_int, [Handle, c_i32, c_i32, c_i32, c_dbl, P_dbl, P_dbl, P_i32]),
+    'af_measure_fp64_peak': (c_int, [c_i32, P_dbl]),
 }
 
 

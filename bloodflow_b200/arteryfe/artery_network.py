@@ -41,7 +41,7 @@ class _JunctionX(np.ndarray):
 
 class ArteryNetwork(object):
 
-    def __init__(self, param, wk_scale=None, device=0):
+    def __init__(self, param, wk_scale=None, device=0, stream=None):
         """artery_network.py:56-130.  ``param`` is a ParamParser (or anything
         with ``.param``, ``.geo``, ``.solution`` dicts).  ``wk_scale`` overrides
         the two hard-coded Windkessel factors of HEAD (0.3, 0.01); it can also
@@ -49,6 +49,7 @@ class ArteryNetwork(object):
         order = param.param['order']
         self.N = 2 ** order - 1
         self.device = device
+        self._stream = stream        # optional cudaStream_t (int) the device work is enqueued on
 
         if 'alpha' in param.param.keys():
             if 'R_term' not in param.param:
@@ -193,7 +194,7 @@ class ArteryNetwork(object):
             R1=[[self.arteries[i].param['R1'] * self.wk_scale[0] for i in self.range_leaf_arteries]],
             R2=[[self.arteries[i].param['R2'] * self.wk_scale[1] for i in self.range_leaf_arteries]],
             CT=[[self.arteries[i].param['CT'] for i in self.range_leaf_arteries]],
-            q_ins=self.q_ins, device=self.device)
+            q_ins=self.q_ins, device=self.device, stream=self._stream)
         for a in existing:
             a._attach(self._dev, self._compact[a.i])
             a.define_solution(q0[a.i], theta)
@@ -336,11 +337,12 @@ class ArteryNetwork(object):
         Nt, Nt_store = self.geo['Nt'], self.sol['Nt_store']
         return np.array([n % (Nt / Nt_store) == 0 for n in range(Nt)], dtype=np.uint8)
 
-    def solve(self, write_output=True):
+    def solve(self, write_output=True, n_steps=None):
         """artery_network.py:857-946.  The whole loop runs on the device; the
         host only enqueues it, then fetches the stored snapshots and writes
         them in the reference's directory layout.  Returns the snapshots as a
-        dict (``t``, ``flow``, ``area``, ``pressure``: [snapshot, artery, vertex])."""
+        dict (``t``, ``flow``, ``area``, ``pressure``: [snapshot, artery, vertex]).
+        ``n_steps`` (not in the reference) stops the loop early."""
         self.define_x()
         if write_output:
             self.dump_metadata()
@@ -354,7 +356,8 @@ class ArteryNetwork(object):
             fields |= _ffi.AF_STORE_PRESSURE
         first_cycle = N_cycles - N_cycles_store
         self._dev.set_store(mask, first_cycle, max(1, int(mask.sum()) * N_cycles_store), fields)
-        self._dev.step(0, N_cycles * Nt)
+        total = N_cycles * Nt if n_steps is None else min(int(n_steps), N_cycles * Nt)
+        self._dev.step(0, total)
         self._dev.sync()
         flags = int(self._dev.get_flags()[0])
         if flags & _ffi.AF_FLAG_ARTERY_NOCONV:

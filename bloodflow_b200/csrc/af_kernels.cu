@@ -1194,3 +1194,46 @@ extern "C" int af_windkessel(af_net* n, int32_t network, int32_t leaf, int32_t k
   if (its) *its = (int32_t)buf[2];
   return AF_OK;
 }
+
+// ---- FP64 peak microbenchmark (roofline denominator) --------------------------------
+__global__ void k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
+  double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int af_measure_fp64_peak(int32_t device, double* tflops) {
+  if (!tflops) return fail(AF_EINVAL, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(AF_ENODEVICE, "no CUDA device");
+  AF_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AF_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  double* d = nullptr;
+  AF_CUDA(cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma_peak<<<blocks, threads>>>(d, 1024);        // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(d); return fail(AF_ECUDA, cudaGetErrorString(e)); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return AF_OK;
+}

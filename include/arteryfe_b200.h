@@ -221,6 +221,10 @@ int af_junction_newton(af_net* net, int32_t network, int32_t junction, const dou
 int af_windkessel(af_net* net, int32_t network, int32_t leaf, int32_t k_max, double tol, double* A_out,
                   double* dex, int32_t* its);
 
+/* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of
+ * the device in TFLOP/s (2 flop per DFMA), the denominator of the FP64 roofline. */
+int af_measure_fp64_peak(int32_t device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif
