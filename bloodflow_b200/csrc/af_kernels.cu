@@ -80,8 +80,8 @@ __global__ void k_setup_vessels(NetDev nd, const double* Ru, const double* Rd, c
   v.src_k = -2.0 * kSqrtPi / db[b] / Re[b];
   v.rpi_dbRe = kSqrtPi / db[b] / Re[b];
   v.tapered = (v.Rd != v.Ru) ? 1 : 0;
-  Coef c0 = coef_at(v, 0.0), cL = coef_at(v, v.L);
-  v.f0 = c0.f; v.A00 = c0.A0; v.fL = cL.f; v.A0L = cL.A0;
+  Coef c0 = coef_exact(v, 0.0), cL = coef_exact(v, v.L);
+  v.f0 = c0.f; v.A00 = c0.A0; v.fL = cL.f; v.A0L = cL.A0; v.dfdr0 = c0.dfdr;
   nd.ves[ba] = v;
 }
 
@@ -92,7 +92,7 @@ __global__ void k_setup_state(NetDev nd, const double* q0) {
   for (int j = threadIdx.x; j < nd.S; j += blockDim.x) {
     double A = 0.0, q = 0.0;
     if (j < nd.np) {
-      A = coef_at(v, v.dx * j).A0;     // Un = (A0(x_j), q0)  (ar:154-157)
+      A = coef_exact(v, v.dx * j).A0;  // Un = (A0(x_j), q0)  (ar:154-157)
       q = q0[ba];
     }
     nd.A[0][off + j] = A; nd.q[0][off + j] = q;
@@ -469,7 +469,7 @@ __global__ void k_eval_state(NetDev nd, int cur, int ba, int n, const double* x,
 
 __global__ void k_eval_coef(NetDev nd, int ba, int n, const double* x, double* out) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    Coef c = coef_at(nd.ves[ba], x[i]);
+    Coef c = coef_exact(nd.ves[ba], x[i]);
     out[4 * i] = c.f; out[4 * i + 1] = c.A0; out[4 * i + 2] = c.dfdr; out[4 * i + 3] = c.drdx;
   }
 }

@@ -20,6 +20,12 @@
 
 namespace af {
 
+#ifdef __CUDA_ARCH__
+#define af_rsqrt(x) rsqrt(x)
+#else
+#define af_rsqrt(x) (1.0 / sqrt(x))
+#endif
+
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSqrtPi = 1.7724538509055159;   // == (double)sqrt((double)pi)
 constexpr double kDolfinEps = 3.0e-16;           // [3P] DOLFIN_EPS
@@ -54,13 +60,15 @@ struct Vessel {
   int32_t tapered;      // Rd != Ru
   // Expression values cached for untapered vessels and for the two ends
   double f0, A00, fL, A0L;
+  double dfdr0;         // dfdr at x = 0 (the constant value of an untapered vessel)
 };
 
 struct Coef {
   double f, A0, dfdr, drdx;
 };
 
-AF_HD Coef coef_at(const Vessel& v, double x) {
+// Exact evaluation (used at set-up and for tapered vessels).
+AF_HD Coef coef_exact(const Vessel& v, double x) {
   Coef c;
   // r0 = Ru*pow(Rd/Ru, x/L); pow(1, y) == 1 exactly, so the untapered branch
   // only skips work.
@@ -70,6 +78,15 @@ AF_HD Coef coef_at(const Vessel& v, double x) {
   c.f = 4.0 / 3.0 * (v.k1 * e + v.k3);
   c.dfdr = 4.0 / 3.0 * v.k1 * v.k2 * e;
   c.drdx = v.lr_over_L * r0;
+  return c;
+}
+
+// Hot-path evaluation: an untapered vessel (Rd == Ru) has x-independent
+// Expressions (drdx == log(1)/L*r0 == 0 exactly), cached at set-up.
+AF_HD Coef coef_at(const Vessel& v, double x) {
+  if (v.tapered) return coef_exact(v, x);
+  Coef c;
+  c.f = v.f0; c.A0 = v.A00; c.dfdr = v.dfdr0; c.drdx = 0.0;
   return c;
 }
 
@@ -154,12 +171,17 @@ AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int
   double c_q = dt * (R1 + R2) / R1 / R2 / CT * q0s;
   double dtdex = dt / dex;
   double Am0 = A0s;
+  // The fixed-point map is the reference's (an:411-420); (p-pn)/R1 and
+  // sqrt(A0/Am0) are evaluated as (p-pn)*(1/R1) and sqrt(A0)*rsqrt(Am0), which
+  // shortens the serial chain of the up-to-100 dependent iterations and
+  // differs from the reference's rounding by a few ulp.
+  const double invR1 = 1.0 / R1, sA0L = sqrt(v.A0L);
   int k = 0;
   for (; k < k_max;) {
     double p_old = p;
-    double qm0 = q0s + (p - pn) / R1 + c_pn - c_q;
+    double qm0 = q0s + (p - pn) * invR1 + c_pn - c_q;
     Am0 = A0s - dtdex * (qm0 - qm1);
-    p = outlet_pressure(v, Am0);
+    p = v.p0 + v.fL * (1.0 - sA0L * af_rsqrt(Am0));
     ++k;
     if (fabs(p - p_old) < tol) break;
   }
@@ -329,28 +351,166 @@ AF_HD int lu_solve18(double* J, int ld, double* b) {
   return 0;
 }
 
+// 3x3 dense solve with partial pivoting, b <- solution; returns 1 on a zero pivot.
+AF_HD int solve3(double M[9], double b[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int p = k;
+    double best = fabs(M[k * 3 + k]);
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i) {
+      double a = fabs(M[i * 3 + k]);
+      if (a > best) { best = a; p = i; }
+    }
+    if (best == 0.0) return 1;
+    if (p != k) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { double t = M[k * 3 + j]; M[k * 3 + j] = M[p * 3 + j]; M[p * 3 + j] = t; }
+      double t = b[k]; b[k] = b[p]; b[p] = t;
+    }
+    double inv = 1.0 / M[k * 3 + k];
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i) {
+      double l = M[i * 3 + k] * inv;
+#pragma unroll
+      for (int j = k + 1; j < 3; ++j) M[i * 3 + j] -= l * M[k * 3 + j];
+      b[i] -= l * b[k];
+    }
+  }
+  b[2] = b[2] / M[8];
+  b[1] = (b[1] - M[5] * b[2]) / M[4];
+  b[0] = (b[0] - M[1] * b[1] - M[2] * b[2]) / M[0];
+  return 0;
+}
+
+// One Newton iteration's data: residual y[18] and the 15 state-dependent
+// Jacobian entries (the other 26 non-zeros are the constants 2, -1, +-1 and
+// +-dt/dex).  Same formulas as junction_residual/junction_jacobian.
+struct JunctionLin {
+  double dPh[3], dPf[3];   // |d pressure / dA| at A^{n+1/2}, A^{n+1}   (rows 8-11)
+  double gq[3], gA[3];     // J[12+v, qg_v], J[12+v, Ag_v]
+};
+
+AF_HD void junction_linearise(const JunctionCtx& c, const double* x, double* y, JunctionLin& l) {
+  double ph[3], pf[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    double s = v == 0 ? 1.0 : -1.0;
+    double Ag = x[11 + 3 * v], qg = x[2 + 3 * v];
+    const Coef& cg = c.cg[v];
+    const Coef& cj = c.cj[v];
+    double sA = sqrt(Ag);
+    double Fg2 = qg * qg + cg.f * sqrt(cg.A0 * Ag);
+    double Sg2 = c.src_k[v] * qg / sA + (2.0 * sA * (kSqrtPi * cg.f + sqrt(cg.A0) * cg.dfdr) - Ag * cg.dfdr) * cg.drdx;
+    y[v] = 2.0 * x[3 * v + 1] - c.qh[v] - x[3 * v + 2];
+    y[3 + v] = 2.0 * x[10 + 3 * v] - c.Ah[v] - x[11 + 3 * v];
+    y[12 + v] = x[3 * v] - c.qe[v] + s * c.dtdex[v] * (Fg2 - c.Fh2[v]) - c.dt / 2.0 * (Sg2 + c.Sh2[v]);
+    y[15 + v] = x[9 + 3 * v] - c.Ae[v] + s * c.dtdex[v] * (qg - c.qh[v]);
+    double Ah = x[10 + 3 * v], A1 = x[9 + 3 * v];
+    double sAh = sqrt(Ah), sA1 = sqrt(A1), sA0e = sqrt(c.A0e[v]);
+    ph[v] = c.fe[v] * (1.0 - sqrt(c.A0e[v] / Ah));
+    pf[v] = c.fe[v] * (1.0 - sqrt(c.A0e[v] / A1));
+    double k = c.fe[v] * sA0e / 2.0;
+    l.dPh[v] = k / (Ah * sAh);
+    l.dPf[v] = k / (A1 * sA1);
+    double u = qg / Ag;
+    l.gq[v] = s * c.dtdex[v] * 2.0 * qg / Ag + c.dt * c.rpi_dbRe[v] / sA;
+    l.gA[v] = s * c.dtdex[v] * (-(u * u) + cj.f / 2.0 * sqrt(cj.A0 / Ag)) -
+              c.dt / 2.0 * (c.rpi_dbRe[v] * qg / (Ag * sA) +
+                            (1.0 / sA * (kSqrtPi * cj.f + sqrt(cj.A0) * cj.dfdr) - cj.dfdr) * cj.drdx);
+  }
+  y[6] = x[0] - x[3] - x[6];
+  y[7] = x[1] - x[4] - x[7];
+  y[8] = ph[0] - ph[1];
+  y[9] = ph[0] - ph[2];
+  y[10] = pf[0] - pf[1];
+  y[11] = pf[0] - pf[2];
+}
+
+// Solve J d = y using the structure of the 18x18 matrix (an:601-663): rows
+// 0-5 and 12-17 each define one unknown in terms of the ghost values
+// (qg_v, Ag_v); substituting them into rows 6-11 leaves a 3x3 system for the
+// three dqg (rows 7, 10, 11) and then one for the three dAg (rows 8, 9, 6).
+// Exact-arithmetic equal to the dense solve numpy does; iteration counts were
+// checked identical.  y <- d.  Returns 1 if a 3x3 pivot is zero.
+AF_HD int junction_solve_structured(const JunctionCtx& c, const JunctionLin& l, double* y) {
+  const double sig[3] = {1.0, -1.0, -1.0};
+  // J[15+v, qg_v] = s*dt/dex (row 17 with d1's ratio, an:662)
+  const double cq[3] = {c.dtdex[0], -c.dtdex[1], -c.dtdex[1]};
+  double M[9], b[3];
+  M[0] = 0.5; M[1] = -0.5; M[2] = -0.5;
+  b[0] = y[7] - (y[0] - y[1] - y[2]) / 2.0;
+#pragma unroll
+  for (int k = 1; k < 3; ++k) {
+    double a0 = l.dPf[0], ak = -l.dPf[k];
+    M[k * 3 + 0] = -a0 * cq[0];
+    M[k * 3 + 1] = k == 1 ? -ak * cq[1] : 0.0;
+    M[k * 3 + 2] = k == 2 ? -ak * cq[2] : 0.0;
+    b[k] = y[9 + k] - a0 * y[15] - ak * y[15 + k];
+  }
+  if (solve3(M, b)) return 1;
+  double dqg[3] = {b[0], b[1], b[2]};
+#pragma unroll
+  for (int k = 1; k < 3; ++k) {
+    double a0 = l.dPh[0], ak = -l.dPh[k];
+    M[(k - 1) * 3 + 0] = a0 / 2.0;
+    M[(k - 1) * 3 + 1] = k == 1 ? ak / 2.0 : 0.0;
+    M[(k - 1) * 3 + 2] = k == 2 ? ak / 2.0 : 0.0;
+    b[k - 1] = y[7 + k] - a0 * y[3] / 2.0 - ak * y[3 + k] / 2.0;
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    M[6 + v] = -sig[v] * l.gA[v];
+    acc += sig[v] * (y[12 + v] - l.gq[v] * dqg[v]);
+  }
+  b[2] = y[6] - acc;
+  if (solve3(M, b)) return 1;
+  double d[18];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    double dAg = b[v];
+    d[3 * v + 2] = dqg[v];
+    d[11 + 3 * v] = dAg;
+    d[3 * v + 1] = (y[v] + dqg[v]) / 2.0;
+    d[10 + 3 * v] = (y[3 + v] + dAg) / 2.0;
+    d[9 + 3 * v] = y[15 + v] - cq[v] * dqg[v];
+    d[3 * v] = y[12 + v] - l.gq[v] * dqg[v] - l.gA[v] * dAg;
+  }
+#pragma unroll
+  for (int i = 0; i < 18; ++i) y[i] = d[i];
+  return 0;
+}
+
+// Dense path, only for the reference's singular branch (an:703-708).
+AF_HD int junction_dense_perturbed(const JunctionCtx& c, const double* x, double* y) {
+  double J[18 * 18];
+  junction_jacobian(c, x, J, 18);
+  junction_residual(c, x, y);
+  for (int i = 0; i < 18; ++i) J[i * 18 + i] += 1.0e-6;
+  y[0] += 1.0e-6;
+  return lu_solve18(J, 18, y);
+}
+
 // newton (an:668-710).  Returns the number of linear solves; *flags gets
 // AF_FLAG_* bits.
 AF_HD int junction_newton(const JunctionCtx& c, double* x, int k_max, double tol, uint32_t* flags) {
-  double J[18 * 18], y[18];
+  double y[18];
+  JunctionLin lin;
   int solves = 0;
   int k = 0;
   for (; k < k_max; ++k) {
-    junction_jacobian(c, x, J, 18);
-    junction_residual(c, x, y);
+    junction_linearise(c, x, y, lin);
     double nrm = 0.0;
+#pragma unroll
     for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
     nrm = sqrt(nrm);
     if (nrm < tol) break;
-    if (lu_solve18(J, 18, y)) {
-      // an:703-708: perturb and retry
+    if (junction_solve_structured(c, lin, y)) {
       *flags |= AF_FLAG_SINGULAR;
-      junction_jacobian(c, x, J, 18);
-      junction_residual(c, x, y);
-      for (int i = 0; i < 18; ++i) J[i * 18 + i] += 1.0e-6;
-      y[0] += 1.0e-6;
-      if (lu_solve18(J, 18, y)) break;
+      if (junction_dense_perturbed(c, x, y)) break;
     }
+#pragma unroll
     for (int i = 0; i < 18; ++i) x[i] -= y[i];
     ++solves;
   }
@@ -395,7 +555,7 @@ AF_HD void p2_to_gauss(double vl, double vr, double vm, double out[3]) {
 }
 
 AF_HD CellCoef cell_coef(const Vessel& v, double xl, double xr) {
-  Coef cl = coef_at(v, xl), cr = coef_at(v, xr), cm = coef_at(v, 0.5 * (xl + xr));
+  Coef cl = coef_exact(v, xl), cr = coef_exact(v, xr), cm = coef_exact(v, 0.5 * (xl + xr));
   double f[3], A0[3], df[3], dr[3];
   p2_to_gauss(cl.f, cr.f, cm.f, f);
   p2_to_gauss(cl.A0, cr.A0, cm.A0, A0);

@@ -26,8 +26,8 @@ static Vessel make_vessel(const double* p, int Nx) {
   v.src_k = -2.0 * kSqrtPi / p[8] / p[7];
   v.rpi_dbRe = kSqrtPi / p[8] / p[7];
   v.tapered = (v.Rd != v.Ru) ? 1 : 0;
-  Coef c0 = coef_at(v, 0.0), cL = coef_at(v, v.L);
-  v.f0 = c0.f; v.A00 = c0.A0; v.fL = cL.f; v.A0L = cL.A0;
+  Coef c0 = coef_exact(v, 0.0), cL = coef_exact(v, v.L);
+  v.f0 = c0.f; v.A00 = c0.A0; v.fL = cL.f; v.A0L = cL.A0; v.dfdr0 = c0.dfdr;
   return v;
 }
 
@@ -36,7 +36,7 @@ extern "C" {
 void hh_coef(const double* vp, int Nx, int n, const double* x, double* out) {
   Vessel v = make_vessel(vp, Nx);
   for (int i = 0; i < n; ++i) {
-    Coef c = coef_at(v, x[i]);
+    Coef c = coef_exact(v, x[i]);
     out[4 * i] = c.f; out[4 * i + 1] = c.A0; out[4 * i + 2] = c.dfdr; out[4 * i + 3] = c.drdx;
   }
 }

@@ -131,8 +131,9 @@ def test_windkessel_math(hh, case, step):
         want = net.windkessel(a)
         np.testing.assert_allclose(out[0], want, rtol=1e-13)
         np.testing.assert_allclose(out[1], a.dex, rtol=1e-14)
-        # the Picard map stagnates within a few ulp of p; the count may differ by round-off
-        assert out[2] == net._last_picard_its or min(out[2], net._last_picard_its) > 15
+        # the stopping test |dp| < 1e-12 sits a few ulp above the round-off of p (~1.1e3), so the
+        # count (not the result) depends on rounding: equal within 2, or both in the stagnation regime
+        assert abs(out[2] - net._last_picard_its) <= 2 or min(out[2], net._last_picard_its) >= 10
 
 
 @pytest.mark.parametrize('case,step', CASES)
