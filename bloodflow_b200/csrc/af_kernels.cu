@@ -210,9 +210,12 @@ __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
 
 // ---------------------------------------------------------------------------
 // per-artery Newton on the theta-scheme weak form: one CTA per artery.
-// Shared memory (doubles, S each): U(A,q) 2 | Un(A,q) 2 | Lo 4 | Dg 4 | Up 4 |
-// R 2 | D1 4 | Rr 2  = 24*S.                              (ar:233-251 + [3P])
+// Shared memory (doubles, S each): U(A,q) 2 | E(A,q) 2 | Lo 4 | Dg 4 | Up 4 |
+// R 2 | cell scratch 5  = 23*S.  Lo/Dg/Up/R are stored in the level-blocked
+// order of the cyclic reduction (af_physics.cuh).            (ar:233-251 + [3P])
 // ---------------------------------------------------------------------------
+#define AF_ARTERY_SMEM_DOUBLES 23
+
 template <int T>
 __device__ __forceinline__ double block_sum(double v, double* red) {
   // fixed-order: lanes by xor-tree, warps in index order
@@ -232,31 +235,29 @@ template <int T>
 __global__ void __launch_bounds__(T) k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   extern __shared__ double sm[];
   __shared__ double red[32];
+  __shared__ CrLayout lay;
   const int S = nd.S, np = nd.np, ne = nd.Nx;
   const int tid = threadIdx.x;
   double* sA = sm;
   double* sq = sA + S;
-  double* sAn = sq + S;
-  double* sqn = sAn + S;
-  double* Lo = sqn + S;
+  double* EA = sq + S;
+  double* Eq = EA + S;
+  double* Lo = Eq + S;
   double* Dg = Lo + 4 * S;
   double* Up = Dg + 4 * S;
   double* R = Up + 4 * S;
-  double* D1 = R + 2 * S;
-  double* Rr = D1 + 4 * S;
+  double* sc = R + 2 * S;
 
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
+  if (tid == 0) cr_layout_init(lay, np);
   {
+    // U <- Un (ar:158; the Newton initial guess is the previous solution)
     const double* gA = nd.A[cur] + off;
     const double* gq = nd.q[cur] + off;
-    for (int i = tid; i < np; i += T) {
-      double x = gA[i], y = gq[i];
-      sA[i] = x; sAn[i] = x;
-      sq[i] = y; sqn[i] = y;
-    }
+    for (int i = tid; i < np; i += T) { sA[i] = gA[i]; sq[i] = gq[i]; }
   }
   const bool root = (a == 0);
   const bool leaf = nd.art_leaf[a] >= 0;
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(T) k_artery(NetDev nd, int cur, int ba0, int i
   const double gAout = nd.bc[ba * 4 + 2], gqout = nd.bc[ba * 4 + 3];
   if (root && inlet_index >= 0) gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
 
-  ArteryConst ac;
-  ac.h = v.dx; ac.dt = nd.dt; ac.theta = nd.theta; ac.Kr = -v.src_k;
+  const double h = v.dx, Kr = -v.src_k;
+  const double dth = nd.dt * nd.theta, dte = nd.dt * (1.0 - nd.theta);
   const double c1_0 = v.f0 * sqrt(v.A00), c1_L = v.fL * sqrt(v.A0L);
   CellCoef ccu;
 #pragma unroll
@@ -279,76 +280,83 @@ __global__ void __launch_bounds__(T) k_artery(NetDev nd, int cur, int ba0, int i
   double r_first = 0.0;
   uint32_t fl = 0;
   for (;;) {
-    // ---- cells: residual + Jacobian blocks --------------------------------
-    for (int e = tid; e < ne; e += T) {
-      CellCoef cc = ccu;
-      if (tab) {
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          cc.c1[g] = tab[(0 + g) * S + e];
-          cc.t2[g] = tab[(3 + g) * S + e];
-          cc.t3[g] = tab[(6 + g) * S + e];
-        }
-      }
-      double rl[2], rr[2], b00[4], b01[4], b10[4], b11[4];
-      cell_assemble<true>(ac, cc, sA[e], sA[e + 1], sq[e], sq[e + 1], sAn[e], sAn[e + 1], sqn[e], sqn[e + 1], rl,
-                          rr, b00, b01, b10, b11);
-      R[e] = rl[0]; R[S + e] = rl[1];
-      Rr[e + 1] = rr[0]; Rr[S + e + 1] = rr[1];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        Dg[c * S + e] = b00[c];
-        Up[c * S + e] = b01[c];
-        Lo[c * S + e + 1] = b10[c];
-        D1[c * S + e + 1] = b11[c];
-      }
-    }
-    __syncthreads();
-    // ---- vertices: sum the two cells, facet terms, Dirichlet rows ----------
+    // ---- assembly: cell integrals, then one row per vertex -------------------
     double part = 0.0;
-    for (int i = tid; i < np; i += T) {
-      double r0 = 0.0, r1 = 0.0, d[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int base = 0; base < np; base += T) {
+      const int i = base + tid;
+      CellInt ci;
+      ci.Gl = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { ci.JA[c] = 0.0; ci.Jq[c] = 0.0; }
       if (i < ne) {
-        r0 = R[i]; r1 = R[S + i];
+        CellCoef cc = ccu;
+        if (tab) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) d[c] = Dg[c * S + i];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Up[c * S + i] = 0.0;
-      }
-      if (i > 0) {
-        r0 += Rr[i]; r1 += Rr[S + i];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) d[c] += D1[c * S + i];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Lo[c * S + i] = 0.0;
-      }
-      if (i == 0 || i == ne) {
-        double rq, dA, dq;
-        facet_term<true>(ac, i == 0 ? c1_0 : c1_L, sA[i], sq[i], sAn[i], sqn[i], rq, dA, dq);
-        r1 += rq; d[2] += dA; d[3] += dq;
-        // [3P] DirichletBC rows: residual = U - g, Jacobian row = identity
-        bool fixA = (i == 0) ? !root : true;
-        bool fixq = (i == 0) ? true : !leaf;
-        double gA = (i == 0) ? gAin : gAout, gq = (i == 0) ? gqin : gqout;
-        if (fixA) {
-          r0 = sA[i] - gA;
-          d[0] = 1.0; d[1] = 0.0;
-          Lo[0 * S + i] = 0.0; Lo[1 * S + i] = 0.0;
-          Up[0 * S + i] = 0.0; Up[1 * S + i] = 0.0;
+          for (int g = 0; g < 3; ++g) {
+            cc.c1[g] = tab[(0 + g) * S + i];
+            cc.t2[g] = tab[(3 + g) * S + i];
+            cc.t3[g] = tab[(6 + g) * S + i];
+          }
         }
-        if (fixq) {
-          r1 = sq[i] - gq;
-          d[2] = 0.0; d[3] = 1.0;
-          Lo[2 * S + i] = 0.0; Lo[3 * S + i] = 0.0;
-          Up[2 * S + i] = 0.0; Up[3 * S + i] = 0.0;
-        }
+        ci = cell_integrals<true>(h, Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
+        sc[0 * S + i + 1] = ci.Gr;
+        sc[1 * S + i + 1] = ci.JA[2];
+        sc[2 * S + i + 1] = ci.JA[3];
+        sc[3 * S + i + 1] = ci.Jq[2];
+        sc[4 * S + i + 1] = ci.Jq[3];
       }
-      R[i] = r0; R[S + i] = r1;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Dg[c * S + i] = d[c];
-      part += r0 * r0 + r1 * r1;
+      __syncthreads();
+      if (i < np) {
+        double Gr_left = 0.0, JAl[4] = {0.0, 0.0, 0.0, 0.0}, Jql[4] = {0.0, 0.0, 0.0, 0.0};
+        if (i > 0) {
+          Gr_left = sc[i];
+          JAl[2] = sc[S + i]; JAl[3] = sc[2 * S + i];
+          Jql[2] = sc[3 * S + i]; Jql[3] = sc[4 * S + i];
+        }
+        const bool end = (i == 0 || i == ne);
+        double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
+        if (end) {
+          PointTerms ft = facet_terms<true>(i == 0 ? c1_0 : c1_L, sA[i], sq[i]);
+          fF2 = ft.F2; fdA = ft.dF2dA; fdq = ft.dF2dq;
+        }
+        VertexX vx = vertex_x(i, ne, h, i > 0 ? sA[i - 1] : 0.0, i > 0 ? sq[i - 1] : 0.0, sA[i], sq[i],
+                              i < ne ? sA[i + 1] : 0.0, i < ne ? sq[i + 1] : 0.0, Gr_left, ci.Gl, fF2);
+        if (it == 0) {          // U == Un: the explicit part of the residual, kept for the whole step
+          EA[i] = -vx.mA + dte * vx.XA;
+          Eq[i] = -vx.mq + dte * vx.Xq;
+        }
+        double r0 = vx.mA + dth * vx.XA + EA[i];
+        double r1 = vx.mq + dth * vx.Xq + Eq[i];
+        VertexRow row = vertex_jacobian(i, ne, h, dth, JAl, Jql, ci.JA, ci.Jq, fdA, fdq);
+        if (end) {
+          // [3P] DirichletBC rows: residual = U - g, Jacobian row = identity
+          const bool fixA = (i == 0) ? !root : true;
+          const bool fixq = (i == 0) ? true : !leaf;
+          const double gA = (i == 0) ? gAin : gAout, gq = (i == 0) ? gqin : gqout;
+          if (fixA) {
+            r0 = sA[i] - gA;
+            row.dg[0] = 1.0; row.dg[1] = 0.0;
+            row.lo[0] = row.lo[1] = row.up[0] = row.up[1] = 0.0;
+          }
+          if (fixq) {
+            r1 = sq[i] - gq;
+            row.dg[2] = 0.0; row.dg[3] = 1.0;
+            row.lo[2] = row.lo[3] = row.up[2] = row.up[3] = 0.0;
+          }
+        }
+        part += r0 * r0 + r1 * r1;
+        const int p = cr_pos(lay, i);
+        if ((i & 1) == 0) {       // eliminated at level 0: store the inverse diagonal
+          double di[4];
+          inv2v(row.dg, di);
+          st2(Dg, S, p, di);
+        } else {
+          st2(Dg, S, p, row.dg);
+        }
+        st2(Lo, S, p, row.lo);
+        st2(Up, S, p, row.up);
+        R[p] = r0; R[S + p] = r1;
+      }
     }
     double r = sqrt(block_sum<T>(part, red));
     // ---- [3P] NewtonSolver::converged ---------------------------------------
@@ -357,18 +365,21 @@ __global__ void __launch_bounds__(T) k_artery(NetDev nd, int cur, int ba0, int i
     if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
     if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
     // ---- block cyclic reduction: J dU = R ----------------------------------
-    int s = 1;
-    for (; 2 * s - 1 < np; s *= 2) {
-      for (int i = 2 * s - 1 + tid * 2 * s; i < np; i += T * 2 * s) cr_forward(i, s, np, Lo, Dg, Up, R, S);
+    const int nlev = lay.nlev;
+    for (int l = 0; (np >> (l + 1)) > 0; ++l) {
+      const int ns = np >> (l + 1);
+      for (int m = tid; m < ns; m += T) cr_forward(lay, l, m, Lo, Dg, Up, R, S);
       __syncthreads();
     }
-    for (; s >= 1; s /= 2) {
-      for (int i = s - 1 + tid * 2 * s; i < np; i += T * 2 * s) cr_backward(i, s, np, Lo, Dg, Up, R, S);
+    for (int l = nlev - 1; l >= 0; --l) {
+      const int cnt = lay.cnt[l];
+      for (int k = tid; k < cnt; k += T) cr_backward(lay, l, k, Lo, Dg, Up, R, S);
       __syncthreads();
     }
     for (int i = tid; i < np; i += T) {
-      sA[i] -= R[i];
-      sq[i] -= R[S + i];
+      const int p = cr_pos(lay, i);
+      sA[i] -= R[p];
+      sq[i] -= R[S + p];
     }
     __syncthreads();
     ++it;
@@ -735,7 +746,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   n->pending.assign(nba, 0);
   // launch configuration
   n->artery_threads = nd.np <= 64 ? 64 : (nd.np <= 160 ? 128 : (nd.np <= 640 ? 256 : 512));
-  n->artery_smem = (size_t)24 * nd.S * sizeof(double);
+  n->artery_smem = (size_t)AF_ARTERY_SMEM_DOUBLES * nd.S * sizeof(double);
   n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
   cudaError_t e;
   switch (n->artery_threads) {

@@ -572,7 +572,8 @@ AF_HD CellCoef cell_coef(const Vessel& v, double xl, double xr) {
   return c;
 }
 
-// F2 = q^2/A + f sqrt(A0 A), S2 (ar:197-222) and their derivatives at one point
+// F2 = q^2/A + f sqrt(A0 A), S2 (ar:197-222) and their derivatives at one point.
+// One reciprocal square root y = A^-1/2 gives sqrt(A) = A*y and 1/A = y*y.
 struct PointTerms {
   double F2, S2, dF2dA, dF2dq, dS2dA, dS2dq;
 };
@@ -580,9 +581,9 @@ struct PointTerms {
 template <bool JAC>
 AF_HD PointTerms point_terms(double A, double q, double c1, double t2, double t3, double Kr) {
   PointTerms t;
-  double inv = 1.0 / A;
-  double sA = sqrt(A);
-  double isA = sA * inv;
+  double isA = af_rsqrt(A);
+  double sA = A * isA;
+  double inv = isA * isA;
   double qi = q * inv;
   t.F2 = q * qi + c1 * sA;
   t.S2 = -Kr * q * isA + 2.0 * sA * t2 - A * t3;
@@ -595,86 +596,172 @@ AF_HD PointTerms point_terms(double A, double q, double c1, double t2, double t3
   return t;
 }
 
-// One cell's contribution.  rl/rr: residual rows (A, q) of its left/right
-// vertex.  b00..b11: 2x2 blocks (row-major: [A-row A-col, A-row q-col, q-row
-// A-col, q-row q-col]) d R[(i)] / d U[(j)], i, j in {left, right}.
+// Flux + source integrals of one cell at state (A, q) with 3-point Gauss:
+//   G_i = int (F2 phi_i' + S2 phi_i) dx      (i = left, right vertex)
+// and, if JAC, the state-dependent q-row Jacobian sums WITHOUT the factor
+// -dt*theta and without the mass matrix:
+//   JA[i][j] = int (dF2dA phi_j phi_i' + dS2dA phi_j phi_i),  Jq[i][j] likewise with d/dq.
+// The new iterate carries DOLFIN_EPS on A (ar:197-201, 215-218).
+struct CellInt {
+  double Gl, Gr;
+  double JA[4], Jq[4];   // [ll, lr, rl, rr]
+};
+
 template <bool JAC>
-AF_HD void cell_assemble(const ArteryConst& ac, const CellCoef& cc, double Al, double Ar, double ql, double qr,
-                         double Anl, double Anr, double qnl, double qnr, double rl[2], double rr[2],
-                         double b00[4], double b01[4], double b10[4], double b11[4]) {
+AF_HD CellInt cell_integrals(double h, double Kr, const CellCoef& cc, double Al, double Ar, double ql, double qr) {
   const double xi[3] = {kXi0, kXi1, kXi2};
   const double wq[3] = {kW0, kW1, kW2};
-  const double h = ac.h, dt = ac.dt, th = ac.theta, om = 1.0 - ac.theta;
-  const double dphi0 = -1.0 / h, dphi1 = 1.0 / h;
-  double qx = (qr - ql) / h, qnx = (qnr - qnl) / h;
-  double dq_mix = dt * (th * qx + om * qnx);
-  rl[0] = rl[1] = rr[0] = rr[1] = 0.0;
-  if (JAC) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) b00[k] = b01[k] = b10[k] = b11[k] = 0.0;
-  }
+  CellInt o;
+  double sF = 0.0, sS0 = 0.0, sS1 = 0.0;
+  double a0 = 0.0, a1 = 0.0, b00 = 0.0, b01 = 0.0, b11 = 0.0;
+  double c0 = 0.0, c1 = 0.0, d00 = 0.0, d01 = 0.0, d11 = 0.0;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    double p0 = 1.0 - xi[g], p1 = xi[g];
-    double w = wq[g] * h;
-    double A = Al * p0 + Ar * p1, q = ql * p0 + qr * p1;
-    double An = Anl * p0 + Anr * p1, qn = qnl * p0 + qnr * p1;
-    PointTerms tn = point_terms<false>(An, qn, cc.c1[g], cc.t2[g], cc.t3[g], ac.Kr);
-    PointTerms t = point_terms<JAC>(A + kDolfinEps, q, cc.c1[g], cc.t2[g], cc.t3[g], ac.Kr);
-    double Fm = dt * (th * t.F2 + om * tn.F2);
-    double Sm = dt * (th * t.S2 + om * tn.S2);
-    double ra = (A - An) + dq_mix;
-    double dq = q - qn;
-    rl[0] += w * (ra * p0);
-    rr[0] += w * (ra * p1);
-    rl[1] += w * (dq * p0 - Fm * dphi0 - Sm * p0);
-    rr[1] += w * (dq * p1 - Fm * dphi1 - Sm * p1);
+    double p0 = 1.0 - xi[g], p1 = xi[g], w = wq[g];
+    double A = Al * p0 + Ar * p1 + kDolfinEps, q = ql * p0 + qr * p1;
+    PointTerms t = point_terms<JAC>(A, q, cc.c1[g], cc.t2[g], cc.t3[g], Kr);
+    sF += w * t.F2;
+    sS0 += w * p0 * t.S2;
+    sS1 += w * p1 * t.S2;
     if (JAC) {
-      double dth = dt * th;
-      // rows of vertex i, columns of vertex j
-      const double pi_[2] = {p0, p1}, dpi_[2] = {dphi0, dphi1};
-      double* blk[2][2] = {{b00, b01}, {b10, b11}};
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          double* b = blk[i][j];
-          double pp = pi_[i] * pi_[j];
-          b[0] += w * pp;
-          b[1] += w * (dth * dpi_[j] * pi_[i]);
-          b[2] -= w * (dth * (t.dF2dA * pi_[j] * dpi_[i] + t.dS2dA * pp));
-          b[3] += w * (pp - dth * (t.dF2dq * pi_[j] * dpi_[i] + t.dS2dq * pp));
-        }
+      double wa = w * t.dF2dA, wb = w * t.dS2dA, wc = w * t.dF2dq, wd = w * t.dS2dq;
+      a0 += wa * p0; a1 += wa * p1;
+      b00 += wb * p0 * p0; b01 += wb * p0 * p1; b11 += wb * p1 * p1;
+      c0 += wc * p0; c1 += wc * p1;
+      d00 += wd * p0 * p0; d01 += wd * p0 * p1; d11 += wd * p1 * p1;
     }
   }
+  // phi_l' = -1/h, phi_r' = +1/h; cell measure h
+  o.Gl = -sF + h * sS0;
+  o.Gr = sF + h * sS1;
+  if (JAC) {
+    o.JA[0] = -a0 + h * b00; o.JA[1] = -a1 + h * b01; o.JA[2] = a0 + h * b01; o.JA[3] = a1 + h * b11;
+    o.Jq[0] = -c0 + h * d00; o.Jq[1] = -c1 + h * d01; o.Jq[2] = c0 + h * d01; o.Jq[3] = c1 + h * d11;
+  }
+  return o;
 }
 
 // Exterior-facet term "+F2*v2*ds" on the q row of an end vertex (ar:197-198,
-// 206-207; no outward normal).  c1v = f(x_v)*sqrt(A0(x_v)).
+// 206-207; no outward normal): F2 and its derivatives at the vertex.
+// c1v = f(x_v)*sqrt(A0(x_v)).
 template <bool JAC>
-AF_HD void facet_term(const ArteryConst& ac, double c1v, double A, double q, double An, double qn, double& rq,
-                      double& dA, double& dq) {
-  PointTerms tn = point_terms<false>(An, qn, c1v, 0.0, 0.0, 0.0);
-  PointTerms t = point_terms<JAC>(A + kDolfinEps, q, c1v, 0.0, 0.0, 0.0);
-  rq = ac.dt * (ac.theta * t.F2 + (1.0 - ac.theta) * tn.F2);
-  if (JAC) {
-    dA = ac.dt * ac.theta * t.dF2dA;
-    dq = ac.dt * ac.theta * t.dF2dq;
+AF_HD PointTerms facet_terms(double c1v, double A, double q) {
+  return point_terms<JAC>(A + kDolfinEps, q, c1v, 0.0, 0.0, 0.0);
+}
+
+// One vertex row of the Newton system from the integrals of its two cells.
+//   left  = integrals of cell i-1 (this vertex is its right vertex), unused at i == 0
+//   own   = integrals of cell i   (this vertex is its left vertex),  unused at i == ne
+// U values of vertices i-1, i, i+1 (um/up unused at the ends).  Closed forms for
+// the mass matrix (h/6 [1 4 1]) and the q_x term (+-1/2).
+// The residual is split as R = I(U) + E(Un)  (SURVEY 9.2):
+//   I = M U + dt*theta*X(U),   E = -M Un + dt*(1-theta)*X(Un),
+//   X_A = int q_x phi_i,  X_q = -G_i + F2|facet.
+struct VertexX {
+  double mA, mq, XA, Xq;
+};
+
+AF_HD VertexX vertex_x(int i, int ne, double h, double Am, double qm, double A0, double q0, double Ap, double qp,
+                       double G_left_r, double G_own_l, double facetF2) {
+  VertexX o;
+  const double h6 = h / 6.0;
+  if (i == 0) {
+    o.mA = h6 * (2.0 * A0 + Ap); o.mq = h6 * (2.0 * q0 + qp);
+    o.XA = 0.5 * (qp - q0);
+    o.Xq = -G_own_l + facetF2;
+  } else if (i == ne) {
+    o.mA = h6 * (Am + 2.0 * A0); o.mq = h6 * (qm + 2.0 * q0);
+    o.XA = 0.5 * (q0 - qm);
+    o.Xq = -G_left_r + facetF2;
+  } else {
+    o.mA = h6 * (Am + 4.0 * A0 + Ap); o.mq = h6 * (qm + 4.0 * q0 + qp);
+    o.XA = 0.5 * (qp - qm);
+    o.Xq = -(G_left_r + G_own_l);
   }
+  return o;
+}
+
+struct VertexRow {
+  double lo[4], dg[4], up[4];
+};
+
+// Jacobian row blocks d R[(i, r)] / d U[(i-1 | i | i+1, c)], before Dirichlet rows.
+AF_HD VertexRow vertex_jacobian(int i, int ne, double h, double dth, const double* JA_left, const double* Jq_left,
+                                const double* JA_own, const double* Jq_own, double facet_dA, double facet_dq) {
+  VertexRow r;
+  const double h6 = h / 6.0;
+  double jA = 0.0, jq = 0.0;
+  if (i > 0) {
+    r.lo[0] = h6; r.lo[1] = -0.5 * dth;
+    r.lo[2] = -dth * JA_left[2]; r.lo[3] = h6 - dth * Jq_left[2];
+    jA += JA_left[3]; jq += Jq_left[3];
+  } else {
+    r.lo[0] = r.lo[1] = r.lo[2] = r.lo[3] = 0.0;
+  }
+  if (i < ne) {
+    r.up[0] = h6; r.up[1] = 0.5 * dth;
+    r.up[2] = -dth * JA_own[1]; r.up[3] = h6 - dth * Jq_own[1];
+    jA += JA_own[0]; jq += Jq_own[0];
+  } else {
+    r.up[0] = r.up[1] = r.up[2] = r.up[3] = 0.0;
+  }
+  const double mdiag = (i == 0 || i == ne) ? 2.0 * h6 : 4.0 * h6;
+  r.dg[0] = mdiag;
+  r.dg[1] = (i == 0) ? -0.5 * dth : (i == ne ? 0.5 * dth : 0.0);
+  r.dg[2] = -dth * jA + dth * facet_dA;
+  r.dg[3] = mdiag - dth * jq + dth * facet_dq;
+  return r;
 }
 
 // ---------------------------------------------------------------------------
-// 2x2-block tridiagonal solve by in-place block cyclic reduction.
-// Arrays are component-major: blk[c*ld + i], c = 0..3 (row-major 2x2), rhs[c*ld + i].
+// 2x2-block tridiagonal solve: block cyclic reduction on a LEVEL-BLOCKED
+// layout.  Vertex i is eliminated at level l = ctz(i+1); all vertices of one
+// level are stored contiguously (block l, index (i+1) >> (l+1)), so every
+// level of the reduction reads and writes unit-stride shared memory.  Rows
+// that are about to be eliminated hold the INVERSE of their diagonal block.
+// Arrays are component-major: blk[c*ld + pos], c = 0..3 (row-major 2x2).
 // ---------------------------------------------------------------------------
-AF_HD void inv2(const double* m, int ld, int i, double o[4]) {
-  double a = m[i], b = m[ld + i], c = m[2 * ld + i], d = m[3 * ld + i];
-  double r = 1.0 / (a * d - b * c);
-  o[0] = d * r; o[1] = -b * r; o[2] = -c * r; o[3] = a * r;
+struct CrLayout {
+  int n, nlev;
+  int off[14], cnt[14];
+};
+
+AF_HD int af_ctz(int x) {
+#ifdef __CUDA_ARCH__
+  return __ffs(x) - 1;
+#else
+  return __builtin_ctz((unsigned)x);
+#endif
+}
+
+AF_HD void cr_layout_init(CrLayout& L, int n) {
+  L.n = n;
+  int off = 0, l = 0;
+  for (; l < 14; ++l) {
+    int c = (n + (1 << l)) >> (l + 1);
+    if (c == 0) break;
+    L.off[l] = off; L.cnt[l] = c;
+    off += c;
+  }
+  L.nlev = l;
+}
+
+AF_HD int cr_pos(const CrLayout& L, int i) {
+  int l = af_ctz(i + 1);
+  return L.off[l] + ((i + 1) >> (l + 1));
 }
 
 AF_HD void ld2(const double* m, int ld, int i, double o[4]) {
   o[0] = m[i]; o[1] = m[ld + i]; o[2] = m[2 * ld + i]; o[3] = m[3 * ld + i];
+}
+
+AF_HD void st2(double* m, int ld, int i, const double o[4]) {
+  m[i] = o[0]; m[ld + i] = o[1]; m[2 * ld + i] = o[2]; m[3 * ld + i] = o[3];
+}
+
+AF_HD void inv2v(const double d[4], double o[4]) {
+  double r = 1.0 / (d[0] * d[3] - d[1] * d[2]);
+  o[0] = d[3] * r; o[1] = -d[1] * r; o[2] = -d[2] * r; o[3] = d[0] * r;
 }
 
 AF_HD void mul2(const double a[4], const double b[4], double o[4]) {
@@ -684,74 +771,89 @@ AF_HD void mul2(const double a[4], const double b[4], double o[4]) {
   o[3] = a[2] * b[1] + a[3] * b[3];
 }
 
-// forward step of level s for node i ((i+1) % 2s == 0): eliminate i-s and i+s
-AF_HD void cr_forward(int i, int s, int n, double* Lo, double* Dg, double* Up, double* R, int ld) {
-  double d[4], r0, r1, lo[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
-  ld2(Dg, ld, i, d);
-  r0 = R[i]; r1 = R[ld + i];
+// Forward step of level l for survivor m (vertex i = 2s(m+1)-1, s = 2^l):
+// eliminate its neighbours i-s, i+s (block l entries m, m+1, which hold inverse
+// diagonals).  If the survivor is eliminated at level l+1 its new diagonal is
+// stored inverted.
+AF_HD void cr_forward(const CrLayout& L, int l, int m, double* Lo, double* Dg, double* Up, double* R, int ld) {
+  const int s = 1 << l;
+  const int i = 2 * s * (m + 1) - 1;
+  const int pi = cr_pos(L, i);
+  const int pj = L.off[l] + m;
+  double d[4], lo[4], up[4] = {0.0, 0.0, 0.0, 0.0};
+  ld2(Dg, ld, pi, d);
+  double r0 = R[pi], r1 = R[ld + pi];
   {
-    int j = i - s;   // always >= 0
-    double inv[4], l[4], al[4], t[4];
-    inv2(Dg, ld, j, inv);
-    ld2(Lo, ld, i, l);
-    mul2(l, inv, al);                 // al = Lo_i * D_j^-1
-    ld2(Up, ld, j, t);
-    double m[4];
-    mul2(al, t, m);
-    d[0] -= m[0]; d[1] -= m[1]; d[2] -= m[2]; d[3] -= m[3];
-    r0 -= al[0] * R[j] + al[1] * R[ld + j];
-    r1 -= al[2] * R[j] + al[3] * R[ld + j];
-    ld2(Lo, ld, j, t);
-    mul2(al, t, m);
-    lo[0] = -m[0]; lo[1] = -m[1]; lo[2] = -m[2]; lo[3] = -m[3];
+    double inv[4], t[4], al[4], mm[4];
+    ld2(Dg, ld, pj, inv);
+    ld2(Lo, ld, pi, t);
+    mul2(t, inv, al);                 // al = Lo_i * D_j^-1
+    ld2(Up, ld, pj, t);
+    mul2(al, t, mm);
+    d[0] -= mm[0]; d[1] -= mm[1]; d[2] -= mm[2]; d[3] -= mm[3];
+    double rj0 = R[pj], rj1 = R[ld + pj];
+    r0 -= al[0] * rj0 + al[1] * rj1;
+    r1 -= al[2] * rj0 + al[3] * rj1;
+    ld2(Lo, ld, pj, t);
+    mul2(al, t, mm);
+    lo[0] = -mm[0]; lo[1] = -mm[1]; lo[2] = -mm[2]; lo[3] = -mm[3];
   }
-  int j = i + s;
-  if (j < n) {
-    double inv[4], u[4], ga[4], t[4], m[4];
-    inv2(Dg, ld, j, inv);
-    ld2(Up, ld, i, u);
-    mul2(u, inv, ga);                 // ga = Up_i * D_j^-1
-    ld2(Lo, ld, j, t);
-    mul2(ga, t, m);
-    d[0] -= m[0]; d[1] -= m[1]; d[2] -= m[2]; d[3] -= m[3];
-    r0 -= ga[0] * R[j] + ga[1] * R[ld + j];
-    r1 -= ga[2] * R[j] + ga[3] * R[ld + j];
-    ld2(Up, ld, j, t);
-    mul2(ga, t, m);
-    up[0] = -m[0]; up[1] = -m[1]; up[2] = -m[2]; up[3] = -m[3];
+  if (m + 1 < L.cnt[l]) {             // vertex i+s exists
+    const int pk = pj + 1;
+    double inv[4], t[4], ga[4], mm[4];
+    ld2(Dg, ld, pk, inv);
+    ld2(Up, ld, pi, t);
+    mul2(t, inv, ga);                 // ga = Up_i * D_k^-1
+    ld2(Lo, ld, pk, t);
+    mul2(ga, t, mm);
+    d[0] -= mm[0]; d[1] -= mm[1]; d[2] -= mm[2]; d[3] -= mm[3];
+    double rk0 = R[pk], rk1 = R[ld + pk];
+    r0 -= ga[0] * rk0 + ga[1] * rk1;
+    r1 -= ga[2] * rk0 + ga[3] * rk1;
+    ld2(Up, ld, pk, t);
+    mul2(ga, t, mm);
+    up[0] = -mm[0]; up[1] = -mm[1]; up[2] = -mm[2]; up[3] = -mm[3];
   }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    Dg[c * ld + i] = d[c];
-    Lo[c * ld + i] = lo[c];
-    Up[c * ld + i] = up[c];
+  if ((m + 1) & 1) {                  // eliminated at level l+1: keep the inverse
+    double di[4];
+    inv2v(d, di);
+    st2(Dg, ld, pi, di);
+  } else {
+    st2(Dg, ld, pi, d);
   }
-  R[i] = r0; R[ld + i] = r1;
+  st2(Lo, ld, pi, lo);
+  st2(Up, ld, pi, up);
+  R[pi] = r0; R[ld + pi] = r1;
 }
 
-// back-substitution of level s for node i ((i+1) % 2s == s): neighbours i-s, i+s are known.
-// The solution overwrites R.
-AF_HD void cr_backward(int i, int s, int n, const double* Lo, const double* Dg, const double* Up, double* R,
-                       int ld) {
-  double r0 = R[i], r1 = R[ld + i];
-  int j = i - s;
-  if (j >= 0) {
-    double l[4];
-    ld2(Lo, ld, i, l);
-    r0 -= l[0] * R[j] + l[1] * R[ld + j];
-    r1 -= l[2] * R[j] + l[3] * R[ld + j];
+// Back-substitution of level l for block entry k (vertex i = (2k+1)s - 1):
+// x_i = D_i^-1 (R_i - Lo_i x_{i-s} - Up_i x_{i+s}); the solution overwrites R.
+AF_HD void cr_backward(const CrLayout& L, int l, int k, const double* Lo, const double* Dg, const double* Up,
+                       double* R, int ld) {
+  const int s = 1 << l;
+  const int i = (2 * k + 1) * s - 1;
+  const int pi = L.off[l] + k;
+  double r0 = R[pi], r1 = R[ld + pi];
+  if (k > 0) {
+    const int pj = cr_pos(L, i - s);
+    double t[4];
+    ld2(Lo, ld, pi, t);
+    double x0 = R[pj], x1 = R[ld + pj];
+    r0 -= t[0] * x0 + t[1] * x1;
+    r1 -= t[2] * x0 + t[3] * x1;
   }
-  j = i + s;
-  if (j < n) {
-    double u[4];
-    ld2(Up, ld, i, u);
-    r0 -= u[0] * R[j] + u[1] * R[ld + j];
-    r1 -= u[2] * R[j] + u[3] * R[ld + j];
+  if (i + s < L.n) {
+    const int pj = cr_pos(L, i + s);
+    double t[4];
+    ld2(Up, ld, pi, t);
+    double x0 = R[pj], x1 = R[ld + pj];
+    r0 -= t[0] * x0 + t[1] * x1;
+    r1 -= t[2] * x0 + t[3] * x1;
   }
   double inv[4];
-  inv2(Dg, ld, i, inv);
-  R[i] = inv[0] * r0 + inv[1] * r1;
-  R[ld + i] = inv[2] * r0 + inv[3] * r1;
+  ld2(Dg, ld, pi, inv);
+  R[pi] = inv[0] * r0 + inv[1] * r1;
+  R[ld + pi] = inv[2] * r0 + inv[3] * r1;
 }
 
 }  // namespace af

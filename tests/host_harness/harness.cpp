@@ -92,18 +92,21 @@ void hh_windkessel(const double* vp, int Nx, const double* A, const double* q, d
   out[0] = r.A_out; out[1] = r.dex; out[2] = r.its;
 }
 
-// Serial stand-in for k_artery.  bc = A_in, q_in, A_out, q_out.  On return A, q
-// hold U.  If Rout/Jout are given, the first assembled residual [np][2] and
-// blocks [3][np][4] (Lo, Dg, Up) are copied out (Dirichlet rows applied).
+// Serial stand-in for k_artery (same phases: cell integrals -> vertex rows ->
+// level-blocked cyclic reduction).  bc = A_in, q_in, A_out, q_out.  On entry A, q
+// hold Un (= the initial guess U); on return they hold U.  If Rout/Jout are given,
+// the first assembled residual [np][2] and blocks [3][np][4] (Lo, Dg, Up; Dirichlet
+// rows applied, true diagonal blocks) are copied out in vertex order.
 int hh_artery_solve(const double* vp, int Nx, double dt, double theta, double* A, double* q, const double* bc,
                     int root, int leaf, double rtol, double atol, int max_it, double* r_last, double* Rout,
                     double* Jout) {
   Vessel v = make_vessel(vp, Nx);
   const int np = Nx + 1, ne = Nx, S = np;
-  std::vector<double> An(A, A + np), qn(q, q + np);
-  std::vector<double> Lo(4 * S), Dg(4 * S), Up(4 * S), R(2 * S), D1(4 * S), Rr(2 * S);
-  ArteryConst ac;
-  ac.h = v.dx; ac.dt = dt; ac.theta = theta; ac.Kr = -v.src_k;
+  std::vector<double> EA(S), Eq(S), Lo(4 * S), Dg(4 * S), Up(4 * S), R(2 * S);
+  std::vector<CellInt> cells(ne);
+  CrLayout lay;
+  cr_layout_init(lay, np);
+  const double h = v.dx, Kr = -v.src_k, dth = dt * theta, dte = dt * (1.0 - theta);
   const double c1_0 = v.f0 * sqrt(v.A00), c1_L = v.fL * sqrt(v.A0L);
   int it = 0;
   double r_first = 0.0, r = 0.0;
@@ -115,72 +118,60 @@ int hh_artery_solve(const double* vp, int Nx, double dt, double theta, double* A
       } else {
         for (int g = 0; g < 3; ++g) { cc.c1[g] = c1_0; cc.t2[g] = 0.0; cc.t3[g] = 0.0; }
       }
-      double rl[2], rr[2], b00[4], b01[4], b10[4], b11[4];
-      cell_assemble<true>(ac, cc, A[e], A[e + 1], q[e], q[e + 1], An[e], An[e + 1], qn[e], qn[e + 1], rl, rr, b00,
-                          b01, b10, b11);
-      R[e] = rl[0]; R[S + e] = rl[1];
-      Rr[e + 1] = rr[0]; Rr[S + e + 1] = rr[1];
-      for (int c = 0; c < 4; ++c) {
-        Dg[c * S + e] = b00[c]; Up[c * S + e] = b01[c];
-        Lo[c * S + e + 1] = b10[c]; D1[c * S + e + 1] = b11[c];
-      }
+      cells[e] = cell_integrals<true>(h, Kr, cc, A[e], A[e + 1], q[e], q[e + 1]);
     }
     double part = 0.0;
     for (int i = 0; i < np; ++i) {
-      double r0 = 0.0, r1 = 0.0, d[4] = {0, 0, 0, 0};
-      if (i < ne) {
-        r0 = R[i]; r1 = R[S + i];
-        for (int c = 0; c < 4; ++c) d[c] = Dg[c * S + i];
-      } else {
-        for (int c = 0; c < 4; ++c) Up[c * S + i] = 0.0;
+      CellInt zero;
+      zero.Gl = zero.Gr = 0.0;
+      for (int c = 0; c < 4; ++c) zero.JA[c] = zero.Jq[c] = 0.0;
+      const CellInt& left = i > 0 ? cells[i - 1] : zero;
+      const CellInt& own = i < ne ? cells[i] : zero;
+      const bool end = (i == 0 || i == ne);
+      double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
+      if (end) {
+        PointTerms ft = facet_terms<true>(i == 0 ? c1_0 : c1_L, A[i], q[i]);
+        fF2 = ft.F2; fdA = ft.dF2dA; fdq = ft.dF2dq;
       }
-      if (i > 0) {
-        r0 += Rr[i]; r1 += Rr[S + i];
-        for (int c = 0; c < 4; ++c) d[c] += D1[c * S + i];
-      } else {
-        for (int c = 0; c < 4; ++c) Lo[c * S + i] = 0.0;
-      }
-      if (i == 0 || i == ne) {
-        double rq, dA, dq;
-        facet_term<true>(ac, i == 0 ? c1_0 : c1_L, A[i], q[i], An[i], qn[i], rq, dA, dq);
-        r1 += rq; d[2] += dA; d[3] += dq;
+      VertexX vx = vertex_x(i, ne, h, i > 0 ? A[i - 1] : 0.0, i > 0 ? q[i - 1] : 0.0, A[i], q[i],
+                            i < ne ? A[i + 1] : 0.0, i < ne ? q[i + 1] : 0.0, left.Gr, own.Gl, fF2);
+      if (it == 0) { EA[i] = -vx.mA + dte * vx.XA; Eq[i] = -vx.mq + dte * vx.Xq; }
+      double r0 = vx.mA + dth * vx.XA + EA[i], r1 = vx.mq + dth * vx.Xq + Eq[i];
+      VertexRow row = vertex_jacobian(i, ne, h, dth, left.JA, left.Jq, own.JA, own.Jq, fdA, fdq);
+      if (end) {
         bool fixA = (i == 0) ? !root : true;
         bool fixq = (i == 0) ? true : !leaf;
         double gA = (i == 0) ? bc[0] : bc[2], gq = (i == 0) ? bc[1] : bc[3];
-        if (fixA) {
-          r0 = A[i] - gA; d[0] = 1.0; d[1] = 0.0;
-          Lo[0 * S + i] = Lo[1 * S + i] = Up[0 * S + i] = Up[1 * S + i] = 0.0;
-        }
-        if (fixq) {
-          r1 = q[i] - gq; d[2] = 0.0; d[3] = 1.0;
-          Lo[2 * S + i] = Lo[3 * S + i] = Up[2 * S + i] = Up[3 * S + i] = 0.0;
-        }
+        if (fixA) { r0 = A[i] - gA; row.dg[0] = 1.0; row.dg[1] = 0.0; row.lo[0] = row.lo[1] = row.up[0] = row.up[1] = 0.0; }
+        if (fixq) { r1 = q[i] - gq; row.dg[2] = 0.0; row.dg[3] = 1.0; row.lo[2] = row.lo[3] = row.up[2] = row.up[3] = 0.0; }
       }
-      R[i] = r0; R[S + i] = r1;
-      for (int c = 0; c < 4; ++c) Dg[c * S + i] = d[c];
       part += r0 * r0 + r1 * r1;
+      if (it == 0 && Rout) { Rout[2 * i] = r0; Rout[2 * i + 1] = r1; }
+      if (it == 0 && Jout)
+        for (int c = 0; c < 4; ++c) {
+          Jout[(0 * np + i) * 4 + c] = row.lo[c];
+          Jout[(1 * np + i) * 4 + c] = row.dg[c];
+          Jout[(2 * np + i) * 4 + c] = row.up[c];
+        }
+      const int p = cr_pos(lay, i);
+      if ((i & 1) == 0) { double di[4]; inv2v(row.dg, di); st2(Dg.data(), S, p, di); }
+      else st2(Dg.data(), S, p, row.dg);
+      st2(Lo.data(), S, p, row.lo);
+      st2(Up.data(), S, p, row.up);
+      R[p] = r0; R[S + p] = r1;
     }
     r = sqrt(part);
-    if (it == 0 && Rout) {
-      for (int i = 0; i < np; ++i) { Rout[2 * i] = R[i]; Rout[2 * i + 1] = R[S + i]; }
-      Rout = nullptr;
-    }
-    if (it == 0 && Jout) {
-      const std::vector<double>* m[3] = {&Lo, &Dg, &Up};
-      for (int k = 0; k < 3; ++k)
-        for (int i = 0; i < np; ++i)
-          for (int c = 0; c < 4; ++c) Jout[(k * np + i) * 4 + c] = (*m[k])[c * S + i];
-      Jout = nullptr;
-    }
     if (it == 0) r_first = r;
     if (r / r_first < rtol || r < atol) break;
     if (!(r == r) || it >= max_it) { it = -1 - it; break; }
-    int s = 1;
-    for (; 2 * s - 1 < np; s *= 2)
-      for (int i = 2 * s - 1; i < np; i += 2 * s) cr_forward(i, s, np, Lo.data(), Dg.data(), Up.data(), R.data(), S);
-    for (; s >= 1; s /= 2)
-      for (int i = s - 1; i < np; i += 2 * s) cr_backward(i, s, np, Lo.data(), Dg.data(), Up.data(), R.data(), S);
-    for (int i = 0; i < np; ++i) { A[i] -= R[i]; q[i] -= R[S + i]; }
+    for (int l = 0; (np >> (l + 1)) > 0; ++l)
+      for (int m = 0; m < (np >> (l + 1)); ++m) cr_forward(lay, l, m, Lo.data(), Dg.data(), Up.data(), R.data(), S);
+    for (int l = lay.nlev - 1; l >= 0; --l)
+      for (int k = 0; k < lay.cnt[l]; ++k) cr_backward(lay, l, k, Lo.data(), Dg.data(), Up.data(), R.data(), S);
+    for (int i = 0; i < np; ++i) {
+      const int p = cr_pos(lay, i);
+      A[i] -= R[p]; q[i] -= R[S + p];
+    }
     ++it;
   }
   if (r_last) *r_last = r;
