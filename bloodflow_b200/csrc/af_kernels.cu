@@ -209,12 +209,20 @@ __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
 }
 
 // ---------------------------------------------------------------------------
-// per-artery Newton on the theta-scheme weak form: one CTA per artery.
-// Shared memory (doubles, S each): U(A,q) 2 | E(A,q) 2 | Lo 4 | Dg 4 | Up 4 |
-// R 2 | cell scratch 5  = 23*S.  Lo/Dg/Up/R are stored in the level-blocked
-// order of the cyclic reduction (af_physics.cuh).            (ar:233-251 + [3P])
+// per-artery Newton on the theta-scheme weak form: one CTA per artery, every
+// thread owns FOUR consecutive vertices.                  (ar:233-251 + [3P])
+//
+// Per Newton pass a thread (1) integrates its four cells, (2) builds its four
+// rows in registers, (3) after the residual test eliminates three of them in
+// registers (levels 0 and 1 of the cyclic reduction; the eliminated vertices
+// are parked in shared memory as x = g - P x_l - Q x_r), (4) hands one reduced
+// row to the level-blocked shared-memory reduction over T rows, and (5)
+// back-substitutes its own vertices.  Shared memory, in doubles (T threads):
+//   U(A,q) 8T | reduced Lo,Dg,Up,R 14T | parked a,b,c 30T   = 52T
+// i.e. 104 KB for the 1001-vertex arteries of the order-8 tree (T = 256), two
+// CTAs per SM, so all 255 arteries are co-resident.
 // ---------------------------------------------------------------------------
-#define AF_ARTERY_SMEM_DOUBLES 23
+#define AF_ARTERY_SMEM_PER_THREAD 52
 
 template <int T>
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -231,155 +239,199 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
+__device__ __forceinline__ void park(double* base, int T, int t, const Elim& e) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { base[c * T + t] = e.P[c]; base[(4 + c) * T + t] = e.Q[c]; }
+  base[8 * T + t] = e.g[0];
+  base[9 * T + t] = e.g[1];
+}
+
+__device__ __forceinline__ Elim unpark(const double* base, int T, int t) {
+  Elim e;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { e.P[c] = base[c * T + t]; e.Q[c] = base[(4 + c) * T + t]; }
+  e.g[0] = base[8 * T + t];
+  e.g[1] = base[9 * T + t];
+  return e;
+}
+
 template <int T>
-__global__ void __launch_bounds__(T) k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
+__global__ void __launch_bounds__(T, (T <= 256 ? 2 : 1))
+k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   extern __shared__ double sm[];
   __shared__ double red[32];
   __shared__ CrLayout lay;
-  const int S = nd.S, np = nd.np, ne = nd.Nx;
+  constexpr int NV = 4 * T;
+  const int np = nd.np, ne = nd.Nx, S = nd.S;
   const int tid = threadIdx.x;
   double* sA = sm;
-  double* sq = sA + S;
-  double* EA = sq + S;
-  double* Eq = EA + S;
-  double* Lo = Eq + S;
-  double* Dg = Lo + 4 * S;
-  double* Up = Dg + 4 * S;
-  double* R = Up + 4 * S;
-  double* sc = R + 2 * S;
+  double* sq = sA + NV;
+  double* Lo = sq + NV;
+  double* Dg = Lo + 4 * T;
+  double* Up = Dg + 4 * T;
+  double* R = Up + 4 * T;
+  double* pa = R + 2 * T;     // parked vertex a (also the cell exchange buffer)
+  double* pb = pa + 10 * T;
+  double* pc = pb + 10 * T;
 
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
-  if (tid == 0) cr_layout_init(lay, np);
+  if (tid == 0) cr_layout_init(lay, T);
   {
     // U <- Un (ar:158; the Newton initial guess is the previous solution)
     const double* gA = nd.A[cur] + off;
     const double* gq = nd.q[cur] + off;
-    for (int i = tid; i < np; i += T) { sA[i] = gA[i]; sq[i] = gq[i]; }
+    for (int i = tid; i < NV; i += T) {
+      sA[i] = i < np ? gA[i] : 1.0;
+      sq[i] = i < np ? gq[i] : 0.0;
+    }
   }
-  const bool root = (a == 0);
-  const bool leaf = nd.art_leaf[a] >= 0;
+  ArteryCtx c;
+  c.ne = ne; c.np = np;
+  c.h = v.dx; c.Kr = -v.src_k;
+  c.dth = nd.dt * nd.theta; c.dte = nd.dt * (1.0 - nd.theta);
+  c.c1_0 = v.f0 * sqrt(v.A00); c.c1_L = v.fL * sqrt(v.A0L);
+  c.root = (a == 0); c.leaf = nd.art_leaf[a] >= 0;
   // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
-  double gAin = nd.bc[ba * 4 + 0], gqin = nd.bc[ba * 4 + 1];
-  const double gAout = nd.bc[ba * 4 + 2], gqout = nd.bc[ba * 4 + 3];
-  if (root && inlet_index >= 0) gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
-
-  const double h = v.dx, Kr = -v.src_k;
-  const double dth = nd.dt * nd.theta, dte = nd.dt * (1.0 - nd.theta);
-  const double c1_0 = v.f0 * sqrt(v.A00), c1_L = v.fL * sqrt(v.A0L);
+  c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
+  c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
+  if (c.root && inlet_index >= 0) c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
   CellCoef ccu;
 #pragma unroll
-  for (int g = 0; g < 3; ++g) { ccu.c1[g] = c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
+  for (int g = 0; g < 3; ++g) { ccu.c1[g] = c.c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
   const int slot = nd.coef_slot[ba];
   const double* tab = slot >= 0 ? nd.cellcoef + (size_t)slot * 9 * S : nullptr;
+  const int i0 = 4 * tid;
+  double EA[4], Eq[4];          // explicit part of the residual of the own vertices
   __syncthreads();
+
+  auto cell = [&](int i) {
+    CellInt ci;
+    cell_zero(ci);
+    if (i < ne) {
+      CellCoef cc = ccu;
+      if (tab) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          cc.c1[g] = tab[(0 + g) * S + i];
+          cc.t2[g] = tab[(3 + g) * S + i];
+          cc.t3[g] = tab[(6 + g) * S + i];
+        }
+      }
+      ci = cell_integrals<true>(c.h, c.Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
+    }
+    return ci;
+  };
 
   int it = 0;
   double r_first = 0.0;
   uint32_t fl = 0;
   for (;;) {
-    // ---- assembly: cell integrals, then one row per vertex -------------------
+    const bool first = (it == 0);
+    // ---- cells and rows ------------------------------------------------------
+    // the last cell first: its right part belongs to the next thread's vertex a
+    CellInt c3 = cell(i0 + 3);
+    pa[0 * T + tid] = c3.Gr;
+    pa[1 * T + tid] = c3.JA[2]; pa[2 * T + tid] = c3.JA[3];
+    pa[3 * T + tid] = c3.Jq[2]; pa[4 * T + tid] = c3.Jq[3];
+    __syncthreads();
+    CellInt prev;
+    cell_zero(prev);
+    if (tid > 0) {
+      prev.Gr = pa[0 * T + tid - 1];
+      prev.JA[2] = pa[1 * T + tid - 1]; prev.JA[3] = pa[2 * T + tid - 1];
+      prev.Jq[2] = pa[3 * T + tid - 1]; prev.Jq[3] = pa[4 * T + tid - 1];
+    }
     double part = 0.0;
-    for (int base = 0; base < np; base += T) {
-      const int i = base + tid;
-      CellInt ci;
-      ci.Gl = 0.0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { ci.JA[c] = 0.0; ci.Jq[c] = 0.0; }
-      if (i < ne) {
-        CellCoef cc = ccu;
-        if (tab) {
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            cc.c1[g] = tab[(0 + g) * S + i];
-            cc.t2[g] = tab[(3 + g) * S + i];
-            cc.t3[g] = tab[(6 + g) * S + i];
-          }
-        }
-        ci = cell_integrals<true>(h, Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
-        sc[0 * S + i + 1] = ci.Gr;
-        sc[1 * S + i + 1] = ci.JA[2];
-        sc[2 * S + i + 1] = ci.JA[3];
-        sc[3 * S + i + 1] = ci.Jq[2];
-        sc[4 * S + i + 1] = ci.Jq[3];
-      }
-      __syncthreads();
-      if (i < np) {
-        double Gr_left = 0.0, JAl[4] = {0.0, 0.0, 0.0, 0.0}, Jql[4] = {0.0, 0.0, 0.0, 0.0};
-        if (i > 0) {
-          Gr_left = sc[i];
-          JAl[2] = sc[S + i]; JAl[3] = sc[2 * S + i];
-          Jql[2] = sc[3 * S + i]; Jql[3] = sc[4 * S + i];
-        }
-        const bool end = (i == 0 || i == ne);
-        double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
-        if (end) {
-          PointTerms ft = facet_terms<true>(i == 0 ? c1_0 : c1_L, sA[i], sq[i]);
-          fF2 = ft.F2; fdA = ft.dF2dA; fdq = ft.dF2dq;
-        }
-        VertexX vx = vertex_x(i, ne, h, i > 0 ? sA[i - 1] : 0.0, i > 0 ? sq[i - 1] : 0.0, sA[i], sq[i],
-                              i < ne ? sA[i + 1] : 0.0, i < ne ? sq[i + 1] : 0.0, Gr_left, ci.Gl, fF2);
-        if (it == 0) {          // U == Un: the explicit part of the residual, kept for the whole step
-          EA[i] = -vx.mA + dte * vx.XA;
-          Eq[i] = -vx.mq + dte * vx.Xq;
-        }
-        double r0 = vx.mA + dth * vx.XA + EA[i];
-        double r1 = vx.mq + dth * vx.Xq + Eq[i];
-        VertexRow row = vertex_jacobian(i, ne, h, dth, JAl, Jql, ci.JA, ci.Jq, fdA, fdq);
-        if (end) {
-          // [3P] DirichletBC rows: residual = U - g, Jacobian row = identity
-          const bool fixA = (i == 0) ? !root : true;
-          const bool fixq = (i == 0) ? true : !leaf;
-          const double gA = (i == 0) ? gAin : gAout, gq = (i == 0) ? gqin : gqout;
-          if (fixA) {
-            r0 = sA[i] - gA;
-            row.dg[0] = 1.0; row.dg[1] = 0.0;
-            row.lo[0] = row.lo[1] = row.up[0] = row.up[1] = 0.0;
-          }
-          if (fixq) {
-            r1 = sq[i] - gq;
-            row.dg[2] = 0.0; row.dg[3] = 1.0;
-            row.lo[2] = row.lo[3] = row.up[2] = row.up[3] = 0.0;
-          }
-        }
-        part += r0 * r0 + r1 * r1;
-        const int p = cr_pos(lay, i);
-        if ((i & 1) == 0) {       // eliminated at level 0: store the inverse diagonal
-          double di[4];
-          inv2v(row.dg, di);
-          st2(Dg, S, p, di);
-        } else {
-          st2(Dg, S, p, row.dg);
-        }
-        st2(Lo, S, p, row.lo);
-        st2(Up, S, p, row.up);
-        R[p] = r0; R[S + p] = r1;
-      }
+    Row ra, rb, rc, rd;
+    {
+      CellInt ck = cell(i0);
+      build_row(c, i0, first, sA, sq, prev, ck, EA[0], Eq[0], ra);
+      part += ra.r[0] * ra.r[0] + ra.r[1] * ra.r[1];
+      prev = ck;
+      ck = cell(i0 + 1);
+      build_row(c, i0 + 1, first, sA, sq, prev, ck, EA[1], Eq[1], rb);
+      part += rb.r[0] * rb.r[0] + rb.r[1] * rb.r[1];
+      prev = ck;
+      ck = cell(i0 + 2);
+      build_row(c, i0 + 2, first, sA, sq, prev, ck, EA[2], Eq[2], rc);
+      part += rc.r[0] * rc.r[0] + rc.r[1] * rc.r[1];
+      build_row(c, i0 + 3, first, sA, sq, ck, c3, EA[3], Eq[3], rd);
+      part += rd.r[0] * rd.r[0] + rd.r[1] * rd.r[1];
     }
     double r = sqrt(block_sum<T>(part, red));
     // ---- [3P] NewtonSolver::converged ---------------------------------------
-    if (it == 0) r_first = r;
+    if (first) r_first = r;
     if (r / r_first < nd.newton_rtol || r < nd.newton_atol) break;
     if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
     if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
-    // ---- block cyclic reduction: J dU = R ----------------------------------
-    const int nlev = lay.nlev;
-    for (int l = 0; (np >> (l + 1)) > 0; ++l) {
-      const int ns = np >> (l + 1);
-      for (int m = tid; m < ns; m += T) cr_forward(lay, l, m, Lo, Dg, Up, R, S);
+    // ---- cyclic reduction, levels 0 and 1 in registers ----------------------
+    {
+      Elim ea = make_elim(ra);
+      park(pa, T, tid, ea);
+      apply_left(rb, ea);
+      Elim ec = make_elim(rc);
+      park(pc, T, tid, ec);
+      apply_right(rb, ec);
+      apply_left(rd, ec);
+    }
+    __syncthreads();
+    if (tid + 1 < T) {
+      Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
+      apply_right(rd, en);
+    }
+    {
+      Elim eb = make_elim(rb);
+      park(pb, T, tid, eb);
+      apply_left(rd, eb);
+    }
+    __syncthreads();
+    if (tid + 1 < T) {
+      Elim en = unpark(pb, T, tid + 1);      // vertex b of the next thread
+      apply_right(rd, en);
+    }
+    // ---- the reduced system (one row per thread), level-blocked --------------
+    {
+      const int p = cr_pos(lay, tid);
+      if ((tid & 1) == 0) {
+        double di[4];
+        inv2v(rd.dg, di);
+        st2(Dg, T, p, di);
+      } else {
+        st2(Dg, T, p, rd.dg);
+      }
+      st2(Lo, T, p, rd.lo);
+      st2(Up, T, p, rd.up);
+      R[p] = rd.r[0]; R[T + p] = rd.r[1];
+    }
+    __syncthreads();
+    for (int l = 0; (T >> (l + 1)) > 0; ++l) {
+      const int ns = T >> (l + 1);
+      if (tid < ns) cr_forward(lay, l, tid, Lo, Dg, Up, R, T);
       __syncthreads();
     }
-    for (int l = nlev - 1; l >= 0; --l) {
-      const int cnt = lay.cnt[l];
-      for (int k = tid; k < cnt; k += T) cr_backward(lay, l, k, Lo, Dg, Up, R, S);
+    for (int l = lay.nlev - 1; l >= 0; --l) {
+      if (tid < lay.cnt[l]) cr_backward(lay, l, tid, Lo, Dg, Up, R, T);
       __syncthreads();
     }
-    for (int i = tid; i < np; i += T) {
-      const int p = cr_pos(lay, i);
-      sA[i] -= R[p];
-      sq[i] -= R[S + p];
+    // ---- back-substitution of the own vertices, U -= dU ----------------------
+    {
+      double xl[2] = {0.0, 0.0}, xd[2], xa[2], xb[2], xc[2];
+      const int p = cr_pos(lay, tid);
+      xd[0] = R[p]; xd[1] = R[T + p];
+      if (tid > 0) {
+        const int pl = cr_pos(lay, tid - 1);
+        xl[0] = R[pl]; xl[1] = R[T + pl];
+      }
+      back_sub(unpark(pb, T, tid), xl, xd, xb);
+      back_sub(unpark(pa, T, tid), xl, xb, xa);
+      back_sub(unpark(pc, T, tid), xb, xd, xc);
+      sA[i0] -= xa[0]; sq[i0] -= xa[1];
+      sA[i0 + 1] -= xb[0]; sq[i0 + 1] -= xb[1];
+      sA[i0 + 2] -= xc[0]; sq[i0 + 2] -= xc[1];
+      sA[i0 + 3] -= xd[0]; sq[i0 + 3] -= xd[1];
     }
     __syncthreads();
     ++it;
@@ -621,10 +673,12 @@ static cudaError_t prepare_artery(af_net* n) {
 
 static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot) {
   switch (n->artery_threads) {
+    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot);
     case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot);
     case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot);
     case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot);
-    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot);
+    case 512: return launch_artery<512>(n, ba0, count, inlet_index, log_slot);
+    default: return launch_artery<1024>(n, ba0, count, inlet_index, log_slot);
   }
 }
 
@@ -745,15 +799,19 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
 
   n->pending.assign(nba, 0);
   // launch configuration
-  n->artery_threads = nd.np <= 64 ? 64 : (nd.np <= 160 ? 128 : (nd.np <= 640 ? 256 : 512));
-  n->artery_smem = (size_t)AF_ARTERY_SMEM_DOUBLES * nd.S * sizeof(double);
+  // four vertices per thread, power-of-two thread count (the reduced system has T rows)
+  n->artery_threads = 32;
+  while (4 * n->artery_threads < nd.np) n->artery_threads *= 2;
+  n->artery_smem = (size_t)AF_ARTERY_SMEM_PER_THREAD * n->artery_threads * sizeof(double);
   n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
   cudaError_t e;
   switch (n->artery_threads) {
+    case 32: e = prepare_artery<32>(n); break;
     case 64: e = prepare_artery<64>(n); break;
     case 128: e = prepare_artery<128>(n); break;
     case 256: e = prepare_artery<256>(n); break;
-    default: e = prepare_artery<512>(n); break;
+    case 512: e = prepare_artery<512>(n); break;
+    default: e = prepare_artery<1024>(n); break;
   }
   if (e != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("artery kernel smem: ") + cudaGetErrorString(e)); }
 

@@ -713,6 +713,140 @@ AF_HD VertexRow vertex_jacobian(int i, int ne, double h, double dth, const doubl
   return r;
 }
 
+// Everything a thread needs to turn cell integrals into the Newton row of a vertex.
+struct ArteryCtx {
+  int ne, np;
+  double h, Kr, dth, dte;     // cell size, 2 sqrt(pi)/(db Re), dt*theta, dt*(1-theta)
+  double c1_0, c1_L;          // f*sqrt(A0) at x = 0 and x = L (facet terms)
+  int root, leaf;
+  double gAin, gqin, gAout, gqout;   // Dirichlet data (ar:171-189)
+};
+
+struct Row {
+  double lo[4], dg[4], up[4], r[2];
+};
+
+AF_HD void row_identity(Row& w) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { w.lo[c] = 0.0; w.up[c] = 0.0; }
+  w.dg[0] = 1.0; w.dg[1] = 0.0; w.dg[2] = 0.0; w.dg[3] = 1.0;
+  w.r[0] = 0.0; w.r[1] = 0.0;
+}
+
+// Newton row of vertex i (residual + 2x2 blocks, Dirichlet rows applied) from
+// the right part of cell i-1 (Gr, JA[2..3], Jq[2..3] in `left`) and the left
+// part of cell i (Gl, JA[0..1], Jq[0..1] in `own`).  sA/sq: the iterate U.
+// On the first pass (U == Un) the explicit part E of the residual is produced,
+// afterwards it is consumed.  Vertices i >= np are padding (identity rows).
+AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* sA, const double* sq,
+                     const CellInt& left, const CellInt& own, double& EA, double& Eq, Row& row) {
+  if (i >= c.np) {
+    row_identity(row);
+    return;
+  }
+  const int ne = c.ne;
+  const bool end = (i == 0 || i == ne);
+  double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
+  if (end) {
+    PointTerms ft = facet_terms<true>(i == 0 ? c.c1_0 : c.c1_L, sA[i], sq[i]);
+    fF2 = ft.F2; fdA = ft.dF2dA; fdq = ft.dF2dq;
+  }
+  VertexX vx = vertex_x(i, ne, c.h, i > 0 ? sA[i - 1] : 0.0, i > 0 ? sq[i - 1] : 0.0, sA[i], sq[i],
+                        i < ne ? sA[i + 1] : 0.0, i < ne ? sq[i + 1] : 0.0, left.Gr, own.Gl, fF2);
+  if (first_pass) {
+    EA = -vx.mA + c.dte * vx.XA;
+    Eq = -vx.mq + c.dte * vx.Xq;
+  }
+  row.r[0] = vx.mA + c.dth * vx.XA + EA;
+  row.r[1] = vx.mq + c.dth * vx.Xq + Eq;
+  VertexRow vr = vertex_jacobian(i, ne, c.h, c.dth, left.JA, left.Jq, own.JA, own.Jq, fdA, fdq);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { row.lo[k] = vr.lo[k]; row.dg[k] = vr.dg[k]; row.up[k] = vr.up[k]; }
+  if (end) {
+    // [3P] DirichletBC rows: residual = U - g, Jacobian row = identity
+    const bool fixA = (i == 0) ? !c.root : true;
+    const bool fixq = (i == 0) ? true : !c.leaf;
+    const double gA = (i == 0) ? c.gAin : c.gAout, gq = (i == 0) ? c.gqin : c.gqout;
+    if (fixA) {
+      row.r[0] = sA[i] - gA;
+      row.dg[0] = 1.0; row.dg[1] = 0.0;
+      row.lo[0] = row.lo[1] = row.up[0] = row.up[1] = 0.0;
+    }
+    if (fixq) {
+      row.r[1] = sq[i] - gq;
+      row.dg[2] = 0.0; row.dg[3] = 1.0;
+      row.lo[2] = row.lo[3] = row.up[2] = row.up[3] = 0.0;
+    }
+  }
+}
+
+AF_HD void cell_zero(CellInt& c) {
+  c.Gl = 0.0; c.Gr = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { c.JA[k] = 0.0; c.Jq[k] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------
+// Register-resident part of the block cyclic reduction.  A thread owns four
+// consecutive vertices (a, b, c, d = 4t .. 4t+3).  Level 0 eliminates a and c,
+// level 1 eliminates b; what remains is one row per thread (vertex d) coupled
+// to the d of the neighbouring threads -- the reduced system that goes through
+// shared memory.  An eliminated vertex is kept as  x = g - P x_left - Q x_right.
+// ---------------------------------------------------------------------------
+struct Elim {
+  double P[4], Q[4], g[2];
+};
+
+AF_HD void mul2(const double a[4], const double b[4], double o[4]) {
+  o[0] = a[0] * b[0] + a[1] * b[2];
+  o[1] = a[0] * b[1] + a[1] * b[3];
+  o[2] = a[2] * b[0] + a[3] * b[2];
+  o[3] = a[2] * b[1] + a[3] * b[3];
+}
+
+AF_HD void inv2v(const double d[4], double o[4]) {
+  double r = 1.0 / (d[0] * d[3] - d[1] * d[2]);
+  o[0] = d[3] * r; o[1] = -d[1] * r; o[2] = -d[2] * r; o[3] = d[0] * r;
+}
+
+AF_HD Elim make_elim(const Row& w) {
+  Elim e;
+  double inv[4];
+  inv2v(w.dg, inv);
+  mul2(inv, w.lo, e.P);
+  mul2(inv, w.up, e.Q);
+  e.g[0] = inv[0] * w.r[0] + inv[1] * w.r[1];
+  e.g[1] = inv[2] * w.r[0] + inv[3] * w.r[1];
+  return e;
+}
+
+// eliminate the LEFT neighbour of row w (coupled through w.lo)
+AF_HD void apply_left(Row& w, const Elim& e) {
+  double m[4];
+  mul2(w.lo, e.Q, m);
+  w.dg[0] -= m[0]; w.dg[1] -= m[1]; w.dg[2] -= m[2]; w.dg[3] -= m[3];
+  w.r[0] -= w.lo[0] * e.g[0] + w.lo[1] * e.g[1];
+  w.r[1] -= w.lo[2] * e.g[0] + w.lo[3] * e.g[1];
+  mul2(w.lo, e.P, m);
+  w.lo[0] = -m[0]; w.lo[1] = -m[1]; w.lo[2] = -m[2]; w.lo[3] = -m[3];
+}
+
+// eliminate the RIGHT neighbour of row w (coupled through w.up)
+AF_HD void apply_right(Row& w, const Elim& e) {
+  double m[4];
+  mul2(w.up, e.P, m);
+  w.dg[0] -= m[0]; w.dg[1] -= m[1]; w.dg[2] -= m[2]; w.dg[3] -= m[3];
+  w.r[0] -= w.up[0] * e.g[0] + w.up[1] * e.g[1];
+  w.r[1] -= w.up[2] * e.g[0] + w.up[3] * e.g[1];
+  mul2(w.up, e.Q, m);
+  w.up[0] = -m[0]; w.up[1] = -m[1]; w.up[2] = -m[2]; w.up[3] = -m[3];
+}
+
+AF_HD void back_sub(const Elim& e, const double xl[2], const double xr[2], double x[2]) {
+  x[0] = e.g[0] - (e.P[0] * xl[0] + e.P[1] * xl[1]) - (e.Q[0] * xr[0] + e.Q[1] * xr[1]);
+  x[1] = e.g[1] - (e.P[2] * xl[0] + e.P[3] * xl[1]) - (e.Q[2] * xr[0] + e.Q[3] * xr[1]);
+}
+
 // ---------------------------------------------------------------------------
 // 2x2-block tridiagonal solve: block cyclic reduction on a LEVEL-BLOCKED
 // layout.  Vertex i is eliminated at level l = ctz(i+1); all vertices of one
@@ -757,18 +891,6 @@ AF_HD void ld2(const double* m, int ld, int i, double o[4]) {
 
 AF_HD void st2(double* m, int ld, int i, const double o[4]) {
   m[i] = o[0]; m[ld + i] = o[1]; m[2 * ld + i] = o[2]; m[3 * ld + i] = o[3];
-}
-
-AF_HD void inv2v(const double d[4], double o[4]) {
-  double r = 1.0 / (d[0] * d[3] - d[1] * d[2]);
-  o[0] = d[3] * r; o[1] = -d[1] * r; o[2] = -d[2] * r; o[3] = d[0] * r;
-}
-
-AF_HD void mul2(const double a[4], const double b[4], double o[4]) {
-  o[0] = a[0] * b[0] + a[1] * b[2];
-  o[1] = a[0] * b[1] + a[1] * b[3];
-  o[2] = a[2] * b[0] + a[3] * b[2];
-  o[3] = a[2] * b[1] + a[3] * b[3];
 }
 
 // Forward step of level l for survivor m (vertex i = 2s(m+1)-1, s = 2^l):

@@ -92,88 +92,118 @@ void hh_windkessel(const double* vp, int Nx, const double* A, const double* q, d
   out[0] = r.A_out; out[1] = r.dex; out[2] = r.its;
 }
 
-// Serial stand-in for k_artery (same phases: cell integrals -> vertex rows ->
-// level-blocked cyclic reduction).  bc = A_in, q_in, A_out, q_out.  On entry A, q
-// hold Un (= the initial guess U); on return they hold U.  If Rout/Jout are given,
-// the first assembled residual [np][2] and blocks [3][np][4] (Lo, Dg, Up; Dirichlet
-// rows applied, true diagonal blocks) are copied out in vertex order.
+// Serial stand-in for k_artery: T "threads" of four vertices each, executed
+// phase by phase in the order the kernel's barriers impose (cells -> rows ->
+// levels 0/1 in "registers" -> reduced level-blocked cyclic reduction ->
+// back-substitution).  bc = A_in, q_in, A_out, q_out.  On entry A, q hold Un (= the
+// initial guess U); on return they hold U.  If Rout/Jout are given, the first
+// assembled residual [np][2] and blocks [3][np][4] (Lo, Dg, Up; Dirichlet rows
+// applied) are copied out in vertex order.
 int hh_artery_solve(const double* vp, int Nx, double dt, double theta, double* A, double* q, const double* bc,
                     int root, int leaf, double rtol, double atol, int max_it, double* r_last, double* Rout,
                     double* Jout) {
   Vessel v = make_vessel(vp, Nx);
-  const int np = Nx + 1, ne = Nx, S = np;
-  std::vector<double> EA(S), Eq(S), Lo(4 * S), Dg(4 * S), Up(4 * S), R(2 * S);
-  std::vector<CellInt> cells(ne);
+  const int np = Nx + 1, ne = Nx;
+  int T = 32;
+  while (4 * T < np) T *= 2;
+  const int NV = 4 * T;
+  std::vector<double> sA(NV, 1.0), sq(NV, 0.0), EA(NV), Eq(NV);
+  for (int i = 0; i < np; ++i) { sA[i] = A[i]; sq[i] = q[i]; }
+  std::vector<double> Lo(4 * T), Dg(4 * T), Up(4 * T), R(2 * T);
+  std::vector<Row> rows(NV);
+  std::vector<Elim> ea(T), eb(T), ec(T);
   CrLayout lay;
-  cr_layout_init(lay, np);
-  const double h = v.dx, Kr = -v.src_k, dth = dt * theta, dte = dt * (1.0 - theta);
-  const double c1_0 = v.f0 * sqrt(v.A00), c1_L = v.fL * sqrt(v.A0L);
+  cr_layout_init(lay, T);
+  ArteryCtx c;
+  c.ne = ne; c.np = np; c.h = v.dx; c.Kr = -v.src_k; c.dth = dt * theta; c.dte = dt * (1.0 - theta);
+  c.c1_0 = v.f0 * sqrt(v.A00); c.c1_L = v.fL * sqrt(v.A0L);
+  c.root = root; c.leaf = leaf;
+  c.gAin = bc[0]; c.gqin = bc[1]; c.gAout = bc[2]; c.gqout = bc[3];
+  auto cell = [&](int i) {
+    CellInt ci;
+    cell_zero(ci);
+    if (i < ne) {
+      CellCoef cc;
+      if (v.tapered) {
+        cc = cell_coef(v, v.dx * i, v.dx * (i + 1));
+      } else {
+        for (int g = 0; g < 3; ++g) { cc.c1[g] = c.c1_0; cc.t2[g] = 0.0; cc.t3[g] = 0.0; }
+      }
+      ci = cell_integrals<true>(c.h, c.Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
+    }
+    return ci;
+  };
   int it = 0;
   double r_first = 0.0, r = 0.0;
   for (;;) {
-    for (int e = 0; e < ne; ++e) {
-      CellCoef cc;
-      if (v.tapered) {
-        cc = cell_coef(v, v.dx * e, v.dx * (e + 1));
-      } else {
-        for (int g = 0; g < 3; ++g) { cc.c1[g] = c1_0; cc.t2[g] = 0.0; cc.t3[g] = 0.0; }
-      }
-      cells[e] = cell_integrals<true>(h, Kr, cc, A[e], A[e + 1], q[e], q[e + 1]);
-    }
+    const bool first = (it == 0);
     double part = 0.0;
-    for (int i = 0; i < np; ++i) {
-      CellInt zero;
-      zero.Gl = zero.Gr = 0.0;
-      for (int c = 0; c < 4; ++c) zero.JA[c] = zero.Jq[c] = 0.0;
-      const CellInt& left = i > 0 ? cells[i - 1] : zero;
-      const CellInt& own = i < ne ? cells[i] : zero;
-      const bool end = (i == 0 || i == ne);
-      double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
-      if (end) {
-        PointTerms ft = facet_terms<true>(i == 0 ? c1_0 : c1_L, A[i], q[i]);
-        fF2 = ft.F2; fdA = ft.dF2dA; fdq = ft.dF2dq;
+    for (int i = 0; i < NV; ++i) {
+      CellInt left;
+      cell_zero(left);
+      if (i > 0) left = cell(i - 1);
+      CellInt own = cell(i);
+      build_row(c, i, first, sA.data(), sq.data(), left, own, EA[i], Eq[i], rows[i]);
+      part += rows[i].r[0] * rows[i].r[0] + rows[i].r[1] * rows[i].r[1];
+      if (first && i < np) {
+        if (Rout) { Rout[2 * i] = rows[i].r[0]; Rout[2 * i + 1] = rows[i].r[1]; }
+        if (Jout)
+          for (int k = 0; k < 4; ++k) {
+            Jout[(0 * np + i) * 4 + k] = rows[i].lo[k];
+            Jout[(1 * np + i) * 4 + k] = rows[i].dg[k];
+            Jout[(2 * np + i) * 4 + k] = rows[i].up[k];
+          }
       }
-      VertexX vx = vertex_x(i, ne, h, i > 0 ? A[i - 1] : 0.0, i > 0 ? q[i - 1] : 0.0, A[i], q[i],
-                            i < ne ? A[i + 1] : 0.0, i < ne ? q[i + 1] : 0.0, left.Gr, own.Gl, fF2);
-      if (it == 0) { EA[i] = -vx.mA + dte * vx.XA; Eq[i] = -vx.mq + dte * vx.Xq; }
-      double r0 = vx.mA + dth * vx.XA + EA[i], r1 = vx.mq + dth * vx.Xq + Eq[i];
-      VertexRow row = vertex_jacobian(i, ne, h, dth, left.JA, left.Jq, own.JA, own.Jq, fdA, fdq);
-      if (end) {
-        bool fixA = (i == 0) ? !root : true;
-        bool fixq = (i == 0) ? true : !leaf;
-        double gA = (i == 0) ? bc[0] : bc[2], gq = (i == 0) ? bc[1] : bc[3];
-        if (fixA) { r0 = A[i] - gA; row.dg[0] = 1.0; row.dg[1] = 0.0; row.lo[0] = row.lo[1] = row.up[0] = row.up[1] = 0.0; }
-        if (fixq) { r1 = q[i] - gq; row.dg[2] = 0.0; row.dg[3] = 1.0; row.lo[2] = row.lo[3] = row.up[2] = row.up[3] = 0.0; }
-      }
-      part += r0 * r0 + r1 * r1;
-      if (it == 0 && Rout) { Rout[2 * i] = r0; Rout[2 * i + 1] = r1; }
-      if (it == 0 && Jout)
-        for (int c = 0; c < 4; ++c) {
-          Jout[(0 * np + i) * 4 + c] = row.lo[c];
-          Jout[(1 * np + i) * 4 + c] = row.dg[c];
-          Jout[(2 * np + i) * 4 + c] = row.up[c];
-        }
-      const int p = cr_pos(lay, i);
-      if ((i & 1) == 0) { double di[4]; inv2v(row.dg, di); st2(Dg.data(), S, p, di); }
-      else st2(Dg.data(), S, p, row.dg);
-      st2(Lo.data(), S, p, row.lo);
-      st2(Up.data(), S, p, row.up);
-      R[p] = r0; R[S + p] = r1;
     }
     r = sqrt(part);
-    if (it == 0) r_first = r;
+    if (first) r_first = r;
     if (r / r_first < rtol || r < atol) break;
     if (!(r == r) || it >= max_it) { it = -1 - it; break; }
-    for (int l = 0; (np >> (l + 1)) > 0; ++l)
-      for (int m = 0; m < (np >> (l + 1)); ++m) cr_forward(lay, l, m, Lo.data(), Dg.data(), Up.data(), R.data(), S);
+    for (int t = 0; t < T; ++t) {          // level 0, own part
+      Row &ra = rows[4 * t], &rb = rows[4 * t + 1], &rc = rows[4 * t + 2], &rd = rows[4 * t + 3];
+      ea[t] = make_elim(ra);
+      apply_left(rb, ea[t]);
+      ec[t] = make_elim(rc);
+      apply_right(rb, ec[t]);
+      apply_left(rd, ec[t]);
+    }
+    for (int t = 0; t < T; ++t) {          // level 0 across threads, level 1 own part
+      Row &rb = rows[4 * t + 1], &rd = rows[4 * t + 3];
+      if (t + 1 < T) apply_right(rd, ea[t + 1]);
+      eb[t] = make_elim(rb);
+      apply_left(rd, eb[t]);
+    }
+    for (int t = 0; t < T; ++t) {          // level 1 across threads, reduced row
+      Row& rd = rows[4 * t + 3];
+      if (t + 1 < T) apply_right(rd, eb[t + 1]);
+      const int p = cr_pos(lay, t);
+      if ((t & 1) == 0) { double di[4]; inv2v(rd.dg, di); st2(Dg.data(), T, p, di); }
+      else st2(Dg.data(), T, p, rd.dg);
+      st2(Lo.data(), T, p, rd.lo);
+      st2(Up.data(), T, p, rd.up);
+      R[p] = rd.r[0]; R[T + p] = rd.r[1];
+    }
+    for (int l = 0; (T >> (l + 1)) > 0; ++l)
+      for (int m = 0; m < (T >> (l + 1)); ++m) cr_forward(lay, l, m, Lo.data(), Dg.data(), Up.data(), R.data(), T);
     for (int l = lay.nlev - 1; l >= 0; --l)
-      for (int k = 0; k < lay.cnt[l]; ++k) cr_backward(lay, l, k, Lo.data(), Dg.data(), Up.data(), R.data(), S);
-    for (int i = 0; i < np; ++i) {
-      const int p = cr_pos(lay, i);
-      A[i] -= R[p]; q[i] -= R[S + p];
+      for (int k = 0; k < lay.cnt[l]; ++k) cr_backward(lay, l, k, Lo.data(), Dg.data(), Up.data(), R.data(), T);
+    for (int t = 0; t < T; ++t) {
+      double xl[2] = {0.0, 0.0}, xd[2], xa[2], xb[2], xc[2];
+      const int p = cr_pos(lay, t);
+      xd[0] = R[p]; xd[1] = R[T + p];
+      if (t > 0) { const int pl = cr_pos(lay, t - 1); xl[0] = R[pl]; xl[1] = R[T + pl]; }
+      back_sub(eb[t], xl, xd, xb);
+      back_sub(ea[t], xl, xb, xa);
+      back_sub(ec[t], xb, xd, xc);
+      const int i0 = 4 * t;
+      sA[i0] -= xa[0]; sq[i0] -= xa[1];
+      sA[i0 + 1] -= xb[0]; sq[i0 + 1] -= xb[1];
+      sA[i0 + 2] -= xc[0]; sq[i0 + 2] -= xc[1];
+      sA[i0 + 3] -= xd[0]; sq[i0 + 3] -= xd[1];
     }
     ++it;
   }
+  for (int i = 0; i < np; ++i) { A[i] = sA[i]; q[i] = sq[i]; }
   if (r_last) *r_last = r;
   return it;
 }
