@@ -144,30 +144,10 @@ __global__ void k_setup_x(NetDev nd, const double* q0) {
 // (lanes = 32 gives every task its own warp for single networks; 1 packs
 // ensembles densely).                                    (an:740-786)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, int j, int log_slot) {
-  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
-  const double* A = nd.A[cur];
-  const double* q = nd.q[cur];
-  // adjust_bifurcation_step (an:713-737)
-  double M = 1.0e300;
-  for (int v = 0; v < 3; ++v) {
-    int ba = b * nd.na + ia[v];
-    size_t off = (size_t)ba * nd.S;
-    double m = junction_cfl(nd.ves[ba], v, A + off, q + off, nd.Nx);
-    M = m < M ? m : M;          // NaN-propagation differs from python's min(); flagged below
-  }
-  double dex = (1.0 + nd.cfl_margin) * nd.dt / M;
-  JunctionCtx c;
-  for (int v = 0; v < 3; ++v) {
-    int ba = b * nd.na + ia[v];
-    size_t off = (size_t)ba * nd.S;
-    junction_prepare_vessel(c, v, nd.ves[ba], A + off, q + off, nd.Nx, nd.dt, dex);
-  }
-  double x[18];
+// common tail of a junction task: write x, the Dirichlet data and the counters
+__device__ __forceinline__ void junction_finish(const NetDev& nd, int b, int j, const int* ia, const double* x,
+                                                double dex, int solves, uint32_t fl, int log_slot) {
   double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
-  for (int i = 0; i < 18; ++i) x[i] = xg[i];
-  uint32_t fl = 0;
-  int solves = junction_newton(c, x, nd.junction_k_max, nd.junction_tol, &fl);
   for (int i = 0; i < 18; ++i) xg[i] = x[i];
   // set_inner_bc (an:762-764)
   int bp = b * nd.na + ia[0], b1 = b * nd.na + ia[1], b2 = b * nd.na + ia[2];
@@ -179,6 +159,113 @@ __device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, 
   if (log_slot >= 0) nd.log_j[(size_t)log_slot * nd.nb * nd.nj + b * nd.nj + j] = solves;
   atomicAdd(&nd.totals[1], (unsigned long long)solves);
   if (fl) atomicOr(&nd.flags[b], fl);
+}
+
+// verbatim dense path (reference formulas, 18x18 LU): owns the singular branch an:703-708
+__device__ __noinline__ int junction_slow_path(const NetDev& nd, int cur, int b, const int* ia, double dex, double* x,
+                                               uint32_t* fl) {
+  JunctionCtx c;
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    size_t off = (size_t)ba * nd.S;
+    junction_prepare_vessel(c, v, nd.ves[ba], nd.A[cur] + off, nd.q[cur] + off, nd.Nx, nd.dt, dex);
+  }
+  return junction_newton(c, x, nd.junction_k_max, nd.junction_tol, fl);
+}
+
+// one thread per junction (ensembles: 32 junctions per warp)
+__device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, int j, int log_slot) {
+  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+  const double* A = nd.A[cur];
+  const double* q = nd.q[cur];
+  // adjust_bifurcation_step (an:713-737)
+  double M = 1.0e300;
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    size_t off = (size_t)ba * nd.S;
+    double m = junction_cfl(nd.ves[ba], v, A + off, q + off, nd.Nx);
+    M = m < M ? m : M;
+  }
+  double dex = (1.0 + nd.cfl_margin) * nd.dt / M;
+  JVessel jv[3];
+  for (int v = 0; v < 3; ++v) {
+    int ba = b * nd.na + ia[v];
+    size_t off = (size_t)ba * nd.S;
+    jvessel_prepare(jv[v], v, nd.ves[ba], A + off, q + off, nd.Nx, nd.dt, dex);
+  }
+  double x[18], x0[18];
+  const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
+  for (int i = 0; i < 18; ++i) x0[i] = x[i] = xg[i];
+  uint32_t fl = 0;
+  int solves = junction_newton_fast(jv, x, nd.junction_k_max, nd.junction_tol, &fl);
+  if (solves < 0) {
+    for (int i = 0; i < 18; ++i) x[i] = x0[i];
+    fl = 0;
+    solves = junction_slow_path(nd, cur, b, ia, dex, x, &fl);
+  }
+  junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot);
+}
+
+// one warp per junction (single networks): lane v < 3 owns vessel v; the 3x3
+// solves are done redundantly by every lane, so no result has to travel back.
+__device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, int log_slot) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int v = lane % 3;
+  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+  const int ba = b * nd.na + ia[v];
+  const size_t off = (size_t)ba * nd.S;
+  const double* A = nd.A[cur] + off;
+  const double* q = nd.q[cur] + off;
+  const Vessel ves = nd.ves[ba];
+  // adjust_bifurcation_step (an:713-737): min over the three vessels
+  double M = junction_cfl(ves, v, A, q, nd.Nx);
+  {
+    double m0 = __shfl_sync(FULL, M, 0), m1 = __shfl_sync(FULL, M, 1), m2 = __shfl_sync(FULL, M, 2);
+    M = 1.0e300;
+    M = m0 < M ? m0 : M; M = m1 < M ? m1 : M; M = m2 < M ? m2 : M;
+  }
+  const double dex = (1.0 + nd.cfl_margin) * nd.dt / M;
+  JVessel jv;
+  jvessel_prepare(jv, v, ves, A, q, nd.Nx, nd.dt, dex);
+  const double dtdex_p = __shfl_sync(FULL, jv.dtdex, 0), dtdex_d1 = __shfl_sync(FULL, jv.dtdex, 1);
+  double x[18], x0[18];
+  const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
+  for (int i = 0; i < 18; ++i) x0[i] = x[i] = xg[i];
+  uint32_t fl = 0;
+  int solves = 0, k = 0;
+  bool singular = false;
+  for (; k < nd.junction_k_max; ++k) {
+    const double xv[6] = {x[3 * v], x[3 * v + 1], x[3 * v + 2], x[9 + 3 * v], x[10 + 3 * v], x[11 + 3 * v]};
+    JVesselLin mine, l[3];
+    jvessel_linearise(jv, xv, mine);
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      l[w].y0 = __shfl_sync(FULL, mine.y0, w); l[w].y3 = __shfl_sync(FULL, mine.y3, w);
+      l[w].y12 = __shfl_sync(FULL, mine.y12, w); l[w].y15 = __shfl_sync(FULL, mine.y15, w);
+      l[w].ph = __shfl_sync(FULL, mine.ph, w); l[w].pf = __shfl_sync(FULL, mine.pf, w);
+      l[w].dPh = __shfl_sync(FULL, mine.dPh, w); l[w].dPf = __shfl_sync(FULL, mine.dPf, w);
+      l[w].gq = __shfl_sync(FULL, mine.gq, w); l[w].gA = __shfl_sync(FULL, mine.gA, w);
+    }
+    double y[18];
+    junction_gather(l, x, y);
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
+    if (sqrt(nrm) < nd.junction_tol) break;
+    if (junction_update(l, dtdex_p, dtdex_d1, y)) { singular = true; break; }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) x[i] -= y[i];
+    ++solves;
+  }
+  if (lane != 0) return;
+  if (k == nd.junction_k_max) fl |= AF_FLAG_JUNCTION_KMAX;
+  if (singular) {
+    for (int i = 0; i < 18; ++i) x[i] = x0[i];
+    fl = 0;
+    solves = junction_slow_path(nd, cur, b, ia, dex, x, &fl);
+  }
+  junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot);
 }
 
 __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int l, int log_slot) {
@@ -197,9 +284,19 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
 
 __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gt % lanes) return;
-  long long task = gt / lanes;
   long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
+  if (lanes == 32) {
+    // one warp per task
+    long long task = gt >> 5;
+    if (task < n_j) {
+      junction_task_warp(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
+    } else if (task < n_j + n_l && (threadIdx.x & 31) == 0) {
+      task -= n_j;
+      leaf_task(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+    }
+    return;
+  }
+  long long task = gt;
   if (task < n_j) {
     junction_task(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
   } else if (task < n_j + n_l) {
@@ -568,7 +665,20 @@ __global__ void k_junction_debug(NetDev nd, int cur, int b, int j, int mode, con
     junction_jacobian(c, x, out + 18, 18);
   } else {
     uint32_t fl = 0;
-    int solves = junction_newton(c, x, k_max, tol, &fl);
+    JVessel jv[3];
+    for (int v = 0; v < 3; ++v) {
+      int ba = b * nd.na + ia[v];
+      size_t off = (size_t)ba * nd.S;
+      jvessel_prepare(jv[v], v, nd.ves[ba], A + off, q + off, nd.Nx, nd.dt, dex3[v]);
+    }
+    double xs[18];
+    for (int i = 0; i < 18; ++i) xs[i] = x[i];
+    int solves = junction_newton_fast(jv, x, k_max, tol, &fl);      // the time loop's solver
+    if (solves < 0) {
+      for (int i = 0; i < 18; ++i) x[i] = xs[i];
+      fl = 0;
+      solves = junction_newton(c, x, k_max, tol, &fl);              // verbatim dense path
+    }
     for (int i = 0; i < 18; ++i) out[i] = x[i];
     out[18] = (double)solves;
     out[19] = (double)fl;

@@ -166,24 +166,43 @@ AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int
   double F10 = bc_flux2(c10, Ah10, qh10), S10 = bc_source2(v, c10, Ah10, qh10);
   double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
   double pn = outlet_pressure(v, A0s);
-  double p = pn;
-  double c_pn = dt / R1 / R2 / CT * pn;
-  double c_q = dt * (R1 + R2) / R1 / R2 / CT * q0s;
-  double dtdex = dt / dex;
-  double Am0 = A0s;
-  // The fixed-point map is the reference's (an:411-420); (p-pn)/R1 and
-  // sqrt(A0/Am0) are evaluated as (p-pn)*(1/R1) and sqrt(A0)*rsqrt(Am0), which
-  // shortens the serial chain of the up-to-100 dependent iterations and
-  // differs from the reference's rounding by a few ulp.
-  const double invR1 = 1.0 / R1, sA0L = sqrt(v.A0L);
+  // Fixed-point map of an:411-420,
+  //   qm0 = q + (p-pn)/R1 + dt/(R1 R2 C) pn - dt (R1+R2)/(R1 R2 C) q,
+  //   Am0 = A - dt/dex (qm0 - qm1),   p = p0 + f(L) (1 - sqrt(A0(L)/Am0)),
+  // with the p-independent terms folded:  Am0 = K2 - K3 p,  p = K4 - K5 rsqrt(Am0).
+  // Two FMAs and one reciprocal square root per iteration on the serial chain;
+  // rounding differs from the reference's expression order by a few ulp.
+  const double c_pn = dt / R1 / R2 / CT * pn;
+  const double c_q = dt * (R1 + R2) / R1 / R2 / CT * q0s;
+  const double dtdex = dt / dex;
+  const double K3 = dtdex / R1;
+  const double K2 = A0s - dtdex * (q0s + c_pn - c_q - qm1) + K3 * pn;
+  const double K5 = v.fL * sqrt(v.A0L);
+  const double K4 = v.p0 + v.fL;
+  double p = pn, p1 = pn, p2 = pn, p3 = pn;   // p_k, p_{k-1}, p_{k-2}, p_{k-3}
+  double Am0 = A0s, Am1 = A0s, Am2 = A0s;     // Am_k, Am_{k-1}, Am_{k-2}
   int k = 0;
-  for (; k < k_max;) {
-    double p_old = p;
-    double qm0 = q0s + (p - pn) * invR1 + c_pn - c_q;
-    Am0 = A0s - dtdex * (qm0 - qm1);
-    p = v.p0 + v.fL * (1.0 - sA0L * af_rsqrt(Am0));
+  while (k < k_max) {
+    p3 = p2; p2 = p1; p1 = p;
+    Am2 = Am1; Am1 = Am0;
+    Am0 = K2 - K3 * p1;
+    p = K4 - K5 * af_rsqrt(Am0);
     ++k;
-    if (fabs(p - p_old) < tol) break;
+    if (fabs(p - p1) < tol) break;
+    // The map is deterministic: once an iterate repeats (round-off limit
+    // cycle of period 2 or 3, 10-40 % of the calls) the remaining iterations
+    // are known exactly, so jump to what iteration k_max would return.
+    int m = (k >= 2 && p == p2) ? 2 : ((k >= 3 && p == p3) ? 3 : 0);
+    if (m) {
+      int j = k_max - k;
+      if (j > 0) {
+        int jj = (j - 1) % m + 1;              // Am_{k+j} == Am_{k-m+jj}
+        int back = m - jj;                     // 0: Am_k, 1: Am_{k-1}, 2: Am_{k-2}
+        Am0 = back == 0 ? Am0 : (back == 1 ? Am1 : Am2);
+      }
+      k = k_max;
+      break;
+    }
   }
   r.A_out = Am0;
   r.dex = dex;
@@ -510,6 +529,135 @@ AF_HD int junction_newton(const JunctionCtx& c, double* x, int k_max, double tol
       *flags |= AF_FLAG_SINGULAR;
       if (junction_dense_perturbed(c, x, y)) break;
     }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) x[i] -= y[i];
+    ++solves;
+  }
+  if (k == k_max) *flags |= AF_FLAG_JUNCTION_KMAX;
+  return solves;
+}
+
+// ---------------------------------------------------------------------------
+// Hot-path form of the same bifurcation system, organised per vessel so that
+// three lanes of a warp can work on the three vessels of one junction.  All
+// sqrt/div of the ghost state are derived from reciprocal square roots (three
+// per vessel and Newton iteration instead of 22 div/sqrt), and everything that
+// does not depend on the iterate x is folded into JVessel once per time step.
+// ---------------------------------------------------------------------------
+struct JVessel {
+  double s;                       // +1 parent outlet, -1 daughter inlet
+  double dt, dtdex, hdt;          // dt, dt/dex, dt/2
+  double qe, Ae, qh, Ah, Fh2, Sh2;
+  double gF, gS1, gS2;            // ghost point:  Fg2 = qg^2 + gF sqrt(Ag),  Sg2 = src_k qg/sqrt(Ag) + gS1 sqrt(Ag) - gS2 Ag
+  double jF, jS1, jS2;            // Jacobian point (an:589-597)
+  double src_k, rk;               // -2 sqrt(pi)/(db Re), sqrt(pi)/(db Re)
+  double fe, sA0e, kP;            // f, sqrt(A0) at the junction end; fe*sA0e/2
+};
+
+struct JVesselLin {
+  double y0, y3, y12, y15;        // rows v, 3+v, 12+v, 15+v of problem_function
+  double ph, pf;                  // pressure terms of rows 8-11
+  double dPh, dPf, gq, gA;        // state-dependent Jacobian entries
+};
+
+AF_HD void jvessel_prepare(JVessel& j, int v, const Vessel& ves, const double* A, const double* q, int Nx,
+                           double dt, double dex) {
+  const double L = ves.L;
+  const double xe = v == 0 ? L : 0.0;
+  const double xi = v == 0 ? L - dex : dex;
+  const double xg = v == 0 ? L + dex / 2.0 : -dex / 2.0;
+  const double xh = v == 0 ? L - dex / 2.0 : dex / 2.0;
+  const double xj = v == 0 ? L + dex : -dex;
+  double Ae, qe, Ai, qi, Ah, qh;
+  interp_state(A, q, Nx, ves.dx, xe, Ae, qe);
+  interp_state(A, q, Nx, ves.dx, xi, Ai, qi);
+  if (v == 0)
+    u_half(ves, dt, xi, xe, Ai, qi, Ae, qe, Ah, qh);
+  else
+    u_half(ves, dt, xe, xi, Ae, qe, Ai, qi, Ah, qh);
+  const Coef ch = coef_at(ves, xh), cg = coef_at(ves, xg), cj = coef_at(ves, xj);
+  j.s = v == 0 ? 1.0 : -1.0;
+  j.dt = dt; j.dtdex = dt / dex; j.hdt = dt / 2.0;
+  j.qe = qe; j.Ae = Ae; j.qh = qh; j.Ah = Ah;
+  j.Fh2 = bc_flux2(ch, Ah, qh);
+  j.Sh2 = bc_source2(ves, ch, Ah, qh);
+  const double sg = sqrt(cg.A0), sj = sqrt(cj.A0);
+  j.gF = cg.f * sg;
+  j.gS1 = 2.0 * (kSqrtPi * cg.f + sg * cg.dfdr) * cg.drdx;
+  j.gS2 = cg.dfdr * cg.drdx;
+  j.jF = cj.f / 2.0 * sj;
+  j.jS1 = (kSqrtPi * cj.f + sj * cj.dfdr) * cj.drdx;
+  j.jS2 = cj.dfdr * cj.drdx;
+  j.src_k = ves.src_k; j.rk = ves.rpi_dbRe;
+  j.fe = v == 0 ? ves.fL : ves.f0;
+  j.sA0e = sqrt(v == 0 ? ves.A0L : ves.A00);
+  j.kP = j.fe * j.sA0e / 2.0;
+}
+
+// xv = the six unknowns of this vessel: q^{n+1}, q^{n+1/2}, q ghost, A^{n+1}, A^{n+1/2}, A ghost
+AF_HD void jvessel_linearise(const JVessel& j, const double xv[6], JVesselLin& o) {
+  const double q1 = xv[0], qh = xv[1], qg = xv[2], A1 = xv[3], Ah = xv[4], Ag = xv[5];
+  const double y = af_rsqrt(Ag), sA = Ag * y, iA = y * y;
+  const double Fg2 = qg * qg + j.gF * sA;
+  const double Sg2 = j.src_k * qg * y + j.gS1 * sA - j.gS2 * Ag;
+  o.y0 = 2.0 * qh - j.qh - qg;
+  o.y3 = 2.0 * Ah - j.Ah - Ag;
+  o.y12 = q1 - j.qe + j.s * j.dtdex * (Fg2 - j.Fh2) - j.hdt * (Sg2 + j.Sh2);
+  o.y15 = A1 - j.Ae + j.s * j.dtdex * (qg - j.qh);
+  const double yh = af_rsqrt(Ah), y1 = af_rsqrt(A1);
+  o.ph = j.fe * (1.0 - j.sA0e * yh);
+  o.pf = j.fe * (1.0 - j.sA0e * y1);
+  o.dPh = j.kP * (yh * yh * yh);
+  o.dPf = j.kP * (y1 * y1 * y1);
+  const double u = qg * iA;
+  o.gq = j.s * j.dtdex * 2.0 * u + j.dt * j.rk * y;
+  o.gA = j.s * j.dtdex * (-(u * u) + j.jF * y) - j.hdt * (j.rk * u * y + (j.jS1 * y - j.jS2));
+}
+
+// Residual vector y[18] from the three vessels' shares.
+AF_HD void junction_gather(const JVesselLin l[3], const double* x, double* y) {
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    y[v] = l[v].y0; y[3 + v] = l[v].y3; y[12 + v] = l[v].y12; y[15 + v] = l[v].y15;
+  }
+  y[6] = x[0] - x[3] - x[6];
+  y[7] = x[1] - x[4] - x[7];
+  y[8] = l[0].ph - l[1].ph;
+  y[9] = l[0].ph - l[2].ph;
+  y[10] = l[0].pf - l[1].pf;
+  y[11] = l[0].pf - l[2].pf;
+}
+
+// One Newton update x -= J^-1 y from the gathered shares (structured solve).
+// Returns 0 ok, 1 if a 3x3 pivot vanished (caller takes the dense path).
+AF_HD int junction_update(const JVesselLin l[3], double dtdex_p, double dtdex_d1, double* y) {
+  JunctionCtx c;                       // only dtdex is read by the structured solve
+  c.dtdex[0] = dtdex_p; c.dtdex[1] = dtdex_d1; c.dtdex[2] = dtdex_d1;
+  JunctionLin lin;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) { lin.dPh[v] = l[v].dPh; lin.dPf[v] = l[v].dPf; lin.gq[v] = l[v].gq; lin.gA[v] = l[v].gA; }
+  return junction_solve_structured(c, lin, y);
+}
+
+// Serial Newton over the three vessels (one thread per junction: ensembles).
+// Returns the number of linear solves, or -1 if a 3x3 pivot vanished (the caller
+// then re-runs the verbatim dense path, which owns the reference's singular branch).
+AF_HD int junction_newton_fast(const JVessel jv[3], double* x, int k_max, double tol, uint32_t* flags) {
+  double y[18];
+  JVesselLin l[3];
+  int solves = 0, k = 0;
+  for (; k < k_max; ++k) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const double xv[6] = {x[3 * v], x[3 * v + 1], x[3 * v + 2], x[9 + 3 * v], x[10 + 3 * v], x[11 + 3 * v]};
+      jvessel_linearise(jv[v], xv, l[v]);
+    }
+    junction_gather(l, x, y);
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
+    if (sqrt(nrm) < tol) break;
+    if (junction_update(l, jv[0].dtdex, jv[1].dtdex, y)) return -1;
 #pragma unroll
     for (int i = 0; i < 18; ++i) x[i] -= y[i];
     ++solves;

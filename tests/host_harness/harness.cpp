@@ -74,11 +74,23 @@ void hh_junction_eval(const double* vp, int Nx, const double* A, const double* q
   junction_jacobian(c, x, J, 18);
 }
 
+// mode 0: hot path (per-vessel rsqrt linearisation + structured solve);
+// mode 1: verbatim dense path (reference formulas, 18x18 LU)
 int hh_junction_newton(const double* vp, int Nx, const double* A, const double* q, double dt, const double* dex,
-                       double* x, int k_max, double tol, unsigned* flags) {
-  JunctionCtx c = make_ctx(vp, Nx, A, q, dt, dex);
+                       double* x, int k_max, double tol, unsigned* flags, int mode) {
   uint32_t fl = 0;
-  int s = junction_newton(c, x, k_max, tol, &fl);
+  int s;
+  if (mode == 1) {
+    JunctionCtx c = make_ctx(vp, Nx, A, q, dt, dex);
+    s = junction_newton(c, x, k_max, tol, &fl);
+  } else {
+    JVessel jv[3];
+    for (int v = 0; v < 3; ++v) {
+      Vessel ves = make_vessel(vp + 10 * v, Nx);
+      jvessel_prepare(jv[v], v, ves, A + v * (Nx + 1), q + v * (Nx + 1), Nx, dt, dex[v]);
+    }
+    s = junction_newton_fast(jv, x, k_max, tol, &fl);
+  }
   *flags = fl;
   return s;
 }

@@ -33,7 +33,7 @@ def hh():
     lib.hh_junction_cfl_dex.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, ctypes.c_double]
     lib.hh_junction_eval.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp, c_dp, c_dp]
     lib.hh_junction_newton.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp, ctypes.c_int,
-                                       ctypes.c_double, ctypes.POINTER(ctypes.c_uint)]
+                                       ctypes.c_double, ctypes.POINTER(ctypes.c_uint), ctypes.c_int]
     lib.hh_windkessel.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                   ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_dp]
     lib.hh_artery_solve.argtypes = [c_dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_dp, c_dp, c_dp,
@@ -109,14 +109,15 @@ def test_junction_math(hh, case, step):
         np.testing.assert_allclose(J, net.jacobian(*ves, xp), rtol=1e-13, atol=0)
         for a in ves:
             a.dex = dex3[0]
-        xs = x.copy()
-        fl = ctypes.c_uint(0)
-        solves = hh.hh_junction_newton(_dp(vp), Nx, _dp(A), _dp(q), net.dt, _dp(dex3), _dp(xs), 30, 1e-10,
-                                       ctypes.byref(fl))
         want = net.newton(*ves, x.copy())
-        assert solves == net._last_junction_solves
-        assert fl.value == 0
-        np.testing.assert_allclose(xs, want, rtol=1e-11)
+        for mode in (0, 1):          # hot path, verbatim dense path
+            xs = x.copy()
+            fl = ctypes.c_uint(0)
+            solves = hh.hh_junction_newton(_dp(vp), Nx, _dp(A), _dp(q), net.dt, _dp(dex3), _dp(xs), 30, 1e-10,
+                                           ctypes.byref(fl), mode)
+            assert solves == net._last_junction_solves
+            assert fl.value == 0
+            np.testing.assert_allclose(xs, want, rtol=1e-11)
 
 
 @pytest.mark.parametrize('case,step', CASES)
