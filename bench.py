@@ -44,25 +44,12 @@ NT_STORE = 100
 
 
 def ensemble_member(order, Nx, Nt, member, N_cycles=4):
-    """Member `member` of the UQ ensemble around the nominal tree: stiffness
-    (k1, k3 common factor), root radius, per-leaf R1, R2, CT sampled as in
-    SURVEY 8(d) C5; member 0 is the nominal network."""
+    """Member `member` of the UQ ensemble around the nominal tree (SURVEY 8(d)
+    perturbation model, bloodflow_b200.ensemble); member 0 is the nominal network."""
     from bloodflow_b200.synthetic import tree_param
+    from bloodflow_b200.ensemble import perturb_param
     p = tree_param(order, Nx=Nx, Nt=Nt, N_cycles=N_cycles, Nt_store=NT_STORE)
-    if member:
-        rng = np.random.Generator(np.random.PCG64(20260000 + member))
-        s = rng.uniform(0.9, 1.1)
-        p.param['k1'] *= s
-        p.param['k3'] *= s
-        r = rng.uniform(0.9, 1.1)
-        p.param['Ru'][0] *= r
-        p.param['Rd'][0] *= r
-        p.param['R_term'] *= r
-        n_l = len(p.param['R1'])
-        p.param['R1'] = p.param['R1'] * rng.uniform(0.8, 1.2, n_l)
-        p.param['R2'] = p.param['R2'] * rng.uniform(0.8, 1.2, n_l)
-        p.param['CT'] = p.param['CT'] * rng.uniform(0.8, 1.2, n_l)
-    return p
+    return perturb_param(p, member) if member else p
 
 
 class ClockSampler(threading.Thread):
@@ -200,6 +187,10 @@ def main():
     ap.add_argument('--Nx', type=int, default=NX)
     ap.add_argument('--Nt', type=int, default=NT)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='tree', choices=('tree', 'c5'),
+                    help="tree: one order-8 tree per GPU (default, the headline config); c5: batched UQ ensemble "
+                         "of order-4 networks (BASELINE config 5), --members per GPU")
+    ap.add_argument('--members', type=int, default=8192)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -221,7 +212,11 @@ def main():
 
     import bloodflow_b200.arteryfe as af
     from bloodflow_b200 import _ffi
-    from bloodflow_b200.engine import DeviceNetwork
+    from bloodflow_b200 import ensemble as en
+
+    if args.workload == 'c5':
+        run_c5(args, rank, local_rank, world, torch, dist)
+        return
 
     K, W = args.steps, max(args.warmup, 3)
     p = ensemble_member(args.order, args.Nx, args.Nt, rank)
@@ -260,21 +255,18 @@ def main():
     phase = phase_times(dev, stream, W + K, args.Nt, torch)
 
     # ---- ensemble statistics: the one collective of the path ---------------------------
-    snaps = dev.fetch_snapshots()
-    op = torch.as_tensor(snaps['outlet_pressure'][:, 0, :], device='cuda')
-    stats = torch.stack([op, op * op, op, op], dim=0)
+    n_snap = dev.snapshot_count()
+    op = en.device_tensor(dev.outlet_pressure_device_ptr(), (n_snap, 1, dev.nl), local_rank)   # zero-copy view
+    moments = en.local_moments(op)
     coll_ms = None
     if world > 1:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.all_reduce(stats[0], op=dist.ReduceOp.SUM)
-        dist.all_reduce(stats[1], op=dist.ReduceOp.SUM)
-        dist.all_reduce(stats[2], op=dist.ReduceOp.MIN)
-        dist.all_reduce(stats[3], op=dist.ReduceOp.MAX)
-        e1.record()
+        e0c, e1c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0c.record()
+        en.reduce_moments(moments)
+        e1c.record()
         torch.cuda.synchronize()
-        coll_ms = e0.elapsed_time(e1)
-    mean_p = (stats[0] / world).mean().item()
+        coll_ms = e0c.elapsed_time(e1c)
+    mean_p = float(en.finalize(moments)['mean'].mean().item())
 
     flags = int(dev.get_flags()[0])
     totals = dev.get_totals()
@@ -323,6 +315,85 @@ def main():
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.order, args.Nx, args.Nt)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c5(args, rank, local_rank, world, torch, dist):
+    """BASELINE config 5: batched ensemble of parameter-perturbed order-4
+    networks (15 arteries x 101 vertices each), `--members` per GPU, weak scaling;
+    NCCL reduction of the outlet-pressure moments at the end."""
+    from bloodflow_b200 import ensemble as en
+    from bloodflow_b200.synthetic import tree_param
+    K, W, M = args.steps, max(args.warmup, 3), args.members
+    Nx, Nt = 100, 2000
+    base = tree_param(4, Nx=Nx, Nt=Nt, N_cycles=2, Nt_store=100)
+    stream = torch.cuda.Stream(device=local_rank)
+    ens = en.EnsembleNetwork(base, M, first_index=rank * M, device=local_rank, stream=stream.cuda_stream)
+    dev = ens.dev
+    ens.configure_store(1, 1)
+    nodes = ens.vertices
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dev.step(0, W)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    dev.step(W, K)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    phase = phase_times(dev, stream, W + K, Nt, torch, n=20)
+    n_snap = dev.snapshot_count()
+    op = en.device_tensor(dev.outlet_pressure_device_ptr(), (n_snap, M, dev.nl), local_rank)
+    moments = en.local_moments(op)
+    coll_ms = None
+    if world > 1:
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        en.reduce_moments(moments)
+        c1.record()
+        torch.cuda.synchronize()
+        coll_ms = c0.elapsed_time(c1)
+    stats = en.finalize(moments)
+    flags = dev.get_flags()
+    totals = dev.get_totals()
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        art_us = phase['artery_us']
+        bytes_per_launch = nodes * 32.0
+        achieved = bytes_per_launch / (art_us * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": world * nodes * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "UQ ensemble (BASELINE config 5): %d perturbed order-4 networks per GPU "
+                                   "(15 arteries x 101 vertices, Nt=2000), %d GPUs" % (M, world),
+                       "members_per_gpu": M, "order": 4, "Nx": Nx, "Nt": Nt, "parallelism": "ensemble-dp%d" % world,
+                       "l2": "state %.0f MB per GPU, streamed from HBM every step" % (nodes * 32 / 1e6)},
+            "cycles_per_sec_all_networks": world * M / (ms_total * 1e-3 / K * Nt),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                         "kernel": "k_artery", "kernel_us": art_us, "kernel_share_of_step": phase['artery_share'],
+                         "algorithmic_bytes_per_launch": bytes_per_launch},
+            "phases_us": phase, "gpu_launches": 2 * K, "clocks": clocks,
+            "status": {"flags_or": int(np.bitwise_or.reduce(flags)), "artery_solves": int(totals[0]),
+                       "junction_solves": int(totals[1]), "picard_its": int(totals[2]),
+                       "collective_ms": coll_ms, "mean_outlet_pressure": float(stats['mean'].mean().item()),
+                       "std_outlet_pressure": float(stats['var'].mean().sqrt().item())},
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -71,6 +71,7 @@ class Artery(object):
         self._b = 0           # ensemble member
         self._own = False
         self._dex_host = None
+        self._in_network = False
 
     # ---- Expressions (ar:110-118): closed forms, used for set-up --------------
     def r0(self, x):
@@ -106,7 +107,7 @@ class Artery(object):
         """ar:121-189.  Stand-alone arteries get their own device network."""
         self.q0, self.theta = q0, theta
         self.pn = _NodalFunction(self.dx, np.full(self.Nx + 1, self.param['p0']))
-        if self._dev is None or self._own:
+        if (self._dev is None and not self._in_network) or self._own:
             self._create_private_device()
 
     def _create_private_device(self):
@@ -122,7 +123,7 @@ class Artery(object):
         self._k, self._b, self._own = 0, 0, True
 
     def _attach(self, dev, k, b=0):
-        self._dev, self._k, self._b, self._own = dev, k, b, False
+        self._dev, self._k, self._b, self._own, self._in_network = dev, k, b, False, True
 
     # ---- state -------------------------------------------------------------------
     @property

@@ -41,7 +41,7 @@ class _JunctionX(np.ndarray):
 
 class ArteryNetwork(object):
 
-    def __init__(self, param, wk_scale=None, device=0, stream=None):
+    def __init__(self, param, wk_scale=None, device=0, stream=None, _host_only=False):
         """artery_network.py:56-130.  ``param`` is a ParamParser (or anything
         with ``.param``, ``.geo``, ``.solution`` dicts).  ``wk_scale`` overrides
         the two hard-coded Windkessel factors of HEAD (0.3, 0.01); it can also
@@ -50,6 +50,7 @@ class ArteryNetwork(object):
         self.N = 2 ** order - 1
         self.device = device
         self._stream = stream        # optional cudaStream_t (int) the device work is enqueued on
+        self._host_only = _host_only  # set-up only (ensemble descriptions, CPU tests); no device handle
 
         if 'alpha' in param.param.keys():
             if 'R_term' not in param.param:
@@ -183,22 +184,41 @@ class ArteryNetwork(object):
                                  "(artery_network.py:111-118)" % ip)
             junctions.append([self._compact[ip], self._compact[i1], self._compact[i2]])
         leaves = [self._compact[i] for i in self.range_leaf_arteries]
-        nd = self.nondim
+        self._description = self.describe(existing, junctions, leaves, q0)
         if self._dev is not None:
             self._dev.close()
-        self._dev = DeviceNetwork(
-            self.geo['Nx'], self.geo['Nt'], theta, self.dt, junctions, leaves,
-            k1=nd['k1'], k2=nd['k2'], k3=nd['k3'], rho=nd['rho'], Re=nd['Re'], db=existing[0].db, p0=nd['p0'],
-            Ru=[[a._Ru for a in existing]], Rd=[[a._Rd for a in existing]], L=[[a._L for a in existing]],
-            q0=[[q0[a.i] for a in existing]],
-            R1=[[self.arteries[i].param['R1'] * self.wk_scale[0] for i in self.range_leaf_arteries]],
-            R2=[[self.arteries[i].param['R2'] * self.wk_scale[1] for i in self.range_leaf_arteries]],
-            CT=[[self.arteries[i].param['CT'] for i in self.range_leaf_arteries]],
-            q_ins=self.q_ins, device=self.device, stream=self._stream)
+        self._dev = self._make_device(self._description)
         for a in existing:
             a._attach(self._dev, self._compact[a.i])
             a.define_solution(q0[a.i], theta)
-        self.x = np.ones([len(self.range_parent_arteries), 18])
+        if self._dev is not None:
+            self.x = np.ones([len(self.range_parent_arteries), 18])
+
+    def describe(self, existing, junctions, leaves, q0):
+        """Flat, nondimensional description of the network: exactly the arrays
+        af_desc takes (include/arteryfe_b200.h).  Also used by the ensemble
+        driver, which stacks perturbed copies of it."""
+        nd = self.nondim
+        return dict(
+            Nx=self.geo['Nx'], Nt=self.geo['Nt'], theta=self.sol['theta'], dt=self.dt,
+            junctions=np.array(junctions, dtype=np.int32).reshape(-1, 3), leaves=np.array(leaves, dtype=np.int32),
+            k1=nd['k1'], k2=nd['k2'], k3=nd['k3'], rho=nd['rho'], Re=nd['Re'], db=existing[0].db, p0=nd['p0'],
+            Ru=np.array([a._Ru for a in existing]), Rd=np.array([a._Rd for a in existing]),
+            L=np.array([a._L for a in existing]), q0=np.array([q0[a.i] for a in existing]),
+            R1=np.array([self.arteries[i].param['R1'] * self.wk_scale[0] for i in self.range_leaf_arteries]),
+            R2=np.array([self.arteries[i].param['R2'] * self.wk_scale[1] for i in self.range_leaf_arteries]),
+            CT=np.array([self.arteries[i].param['CT'] for i in self.range_leaf_arteries]),
+            q_ins=self.q_ins)
+
+    def _make_device(self, d):
+        if self._host_only:
+            return None
+        return DeviceNetwork(
+            d['Nx'], d['Nt'], d['theta'], d['dt'], d['junctions'], d['leaves'],
+            k1=d['k1'], k2=d['k2'], k3=d['k3'], rho=d['rho'], Re=d['Re'], db=d['db'], p0=d['p0'],
+            Ru=d['Ru'][None], Rd=d['Rd'][None], L=d['L'][None], q0=d['q0'][None],
+            R1=d['R1'][None], R2=d['R2'][None], CT=d['CT'][None],
+            q_ins=d['q_ins'], device=self.device, stream=self._stream)
 
     @property
     def x(self):
