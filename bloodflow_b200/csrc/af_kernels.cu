@@ -54,6 +54,7 @@ struct NetDev {
   double newton_rtol, newton_atol;
   int newton_max_it, junction_k_max, picard_k_max;
   double junction_tol, picard_tol, cfl_margin;
+  CrLayout lay;          // level-blocked layout of the T-row reduced system of k_artery
   // per-step counter log
   int* log_art;
   int* log_j;
@@ -352,12 +353,95 @@ __device__ __forceinline__ Elim unpark(const double* base, int T, int t) {
   return e;
 }
 
+template <bool JAC>
+__device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
+                                               const double* sA, const double* sq, int i) {
+  CellInt ci;
+  cell_zero(ci);
+  if (i < c.ne) {
+    CellCoef cc = ccu;
+    if (tab) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        cc.c1[g] = tab[(0 + g) * S + i];
+        cc.t2[g] = tab[(3 + g) * S + i];
+        cc.t3[g] = tab[(6 + g) * S + i];
+      }
+    }
+    ci = cell_integrals<JAC>(c.h, c.Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
+  }
+  return ci;
+}
+
+// One assembly pass of a thread: its four cells and four vertex rows, streamed so
+// that at most two rows are live: a and c are turned into their eliminated form
+// (x = g - P x_l - Q x_r, parked in shared memory) as soon as they are complete
+// and applied to b and d (level 0 of the cyclic reduction, own part).  This is
+// done before the convergence test is known; on the converged pass it is
+// discarded.  The right part of the last cell travels to the next thread through
+// `xch` (one CTA barrier).  Returns the thread's share of ||R||^2.
+template <int T, bool JAC>
+__device__ __forceinline__ double assemble_pass(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
+                                                const double* sA, const double* sq, double* xch, double* pa,
+                                                double* pc, bool first, double* EA, double* Eq, Row& rb, Row& rd) {
+  const int tid = threadIdx.x, i0 = 4 * tid;
+  // the last cell first: its right part belongs to the next thread's vertex a
+  CellInt c3 = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0 + 3);
+  xch[0 * T + tid] = c3.Gr;
+  if (JAC) {
+    xch[1 * T + tid] = c3.JA[2]; xch[2 * T + tid] = c3.JA[3];
+    xch[3 * T + tid] = c3.Jq[2]; xch[4 * T + tid] = c3.Jq[3];
+  }
+  __syncthreads();
+  CellInt prev;
+  cell_zero(prev);
+  if (tid > 0) {
+    prev.Gr = xch[0 * T + tid - 1];
+    if (JAC) {
+      prev.JA[2] = xch[1 * T + tid - 1]; prev.JA[3] = xch[2 * T + tid - 1];
+      prev.Jq[2] = xch[3 * T + tid - 1]; prev.Jq[3] = xch[4 * T + tid - 1];
+    }
+  }
+  double part = 0.0;
+  CellInt ck = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0);
+  {
+    Row ra;
+    build_row<JAC>(c, i0, first, sA, sq, prev, ck, EA[0], Eq[0], ra);
+    part += ra.r[0] * ra.r[0] + ra.r[1] * ra.r[1];
+    prev = ck;
+    ck = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0 + 1);
+    build_row<JAC>(c, i0 + 1, first, sA, sq, prev, ck, EA[1], Eq[1], rb);
+    part += rb.r[0] * rb.r[0] + rb.r[1] * rb.r[1];
+    if (JAC) {
+      Elim ea = make_elim(ra);
+      park(pa, T, tid, ea);
+      apply_left(rb, ea);
+    }
+  }
+  prev = ck;
+  ck = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0 + 2);
+  {
+    Row rc;
+    build_row<JAC>(c, i0 + 2, first, sA, sq, prev, ck, EA[2], Eq[2], rc);
+    part += rc.r[0] * rc.r[0] + rc.r[1] * rc.r[1];
+    build_row<JAC>(c, i0 + 3, first, sA, sq, ck, c3, EA[3], Eq[3], rd);
+    part += rd.r[0] * rd.r[0] + rd.r[1] * rd.r[1];
+    if (JAC) {
+      Elim ec = make_elim(rc);
+      park(pc, T, tid, ec);
+      apply_right(rb, ec);
+      apply_left(rd, ec);
+    }
+  }
+  return part;
+}
+
 template <int T>
-__global__ void __launch_bounds__(T, (T <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(T, (T <= 256 ? 512 / T : 1))
 k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   extern __shared__ double sm[];
   __shared__ double red[32];
-  __shared__ CrLayout lay;
+  const CrLayout& lay = nd.lay;
   constexpr int NV = 4 * T;
   const int np = nd.np, ne = nd.Nx, S = nd.S;
   const int tid = threadIdx.x;
@@ -375,7 +459,6 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   const int b = ba / nd.na, a = ba % nd.na;
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
-  if (tid == 0) cr_layout_init(lay, T);
   {
     // U <- Un (ar:158; the Newton initial guess is the previous solution)
     const double* gA = nd.A[cur] + off;
@@ -404,77 +487,33 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   double EA[4], Eq[4];          // explicit part of the residual of the own vertices
   __syncthreads();
 
-  auto cell = [&](int i) {
-    CellInt ci;
-    cell_zero(ci);
-    if (i < ne) {
-      CellCoef cc = ccu;
-      if (tab) {
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          cc.c1[g] = tab[(0 + g) * S + i];
-          cc.t2[g] = tab[(3 + g) * S + i];
-          cc.t3[g] = tab[(6 + g) * S + i];
-        }
-      }
-      ci = cell_integrals<true>(c.h, c.Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
-    }
-    return ci;
-  };
-
   int it = 0;
   double r_first = 0.0;
   uint32_t fl = 0;
+  bool redo = false;
   for (;;) {
     const bool first = (it == 0);
-    // ---- cells and rows ------------------------------------------------------
-    // the last cell first: its right part belongs to the next thread's vertex a
-    CellInt c3 = cell(i0 + 3);
-    pa[0 * T + tid] = c3.Gr;
-    pa[1 * T + tid] = c3.JA[2]; pa[2 * T + tid] = c3.JA[3];
-    pa[3 * T + tid] = c3.Jq[2]; pa[4 * T + tid] = c3.Jq[3];
-    __syncthreads();
-    CellInt prev;
-    cell_zero(prev);
-    if (tid > 0) {
-      prev.Gr = pa[0 * T + tid - 1];
-      prev.JA[2] = pa[1 * T + tid - 1]; prev.JA[3] = pa[2 * T + tid - 1];
-      prev.Jq[2] = pa[3 * T + tid - 1]; prev.Jq[3] = pa[4 * T + tid - 1];
-    }
-    double part = 0.0;
-    Row ra, rb, rc, rd;
-    {
-      CellInt ck = cell(i0);
-      build_row(c, i0, first, sA, sq, prev, ck, EA[0], Eq[0], ra);
-      part += ra.r[0] * ra.r[0] + ra.r[1] * ra.r[1];
-      prev = ck;
-      ck = cell(i0 + 1);
-      build_row(c, i0 + 1, first, sA, sq, prev, ck, EA[1], Eq[1], rb);
-      part += rb.r[0] * rb.r[0] + rb.r[1] * rb.r[1];
-      prev = ck;
-      ck = cell(i0 + 2);
-      build_row(c, i0 + 2, first, sA, sq, prev, ck, EA[2], Eq[2], rc);
-      part += rc.r[0] * rc.r[0] + rc.r[1] * rc.r[1];
-      build_row(c, i0 + 3, first, sA, sq, ck, c3, EA[3], Eq[3], rd);
-      part += rd.r[0] * rd.r[0] + rd.r[1] * rd.r[1];
-    }
-    double r = sqrt(block_sum<T>(part, red));
+    // The Jacobian is assembled together with the residual while a further
+    // Newton step is likely (it < 2: 1.7 steps on average); later passes are
+    // usually the converged one, so they assemble the residual only and are
+    // repeated with the Jacobian in the rare case the test fails.
+    const bool jac = (it < 2) || redo;
+    // ---- cells, rows, level 0 of the reduction (own part) -----------------------
+    double part;
+    Row rb, rd;
+    if (jac)
+      part = assemble_pass<T, true>(c, ccu, tab, S, sA, sq, pb, pa, pc, first, EA, Eq, rb, rd);
+    else
+      part = assemble_pass<T, false>(c, ccu, tab, S, sA, sq, pb, pa, pc, first, EA, Eq, rb, rd);
+    double r = sqrt(block_sum<T>(part, red));     // its two barriers also publish pa/pc
     // ---- [3P] NewtonSolver::converged ---------------------------------------
     if (first) r_first = r;
     if (r / r_first < nd.newton_rtol || r < nd.newton_atol) break;
     if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
     if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
-    // ---- cyclic reduction, levels 0 and 1 in registers ----------------------
-    {
-      Elim ea = make_elim(ra);
-      park(pa, T, tid, ea);
-      apply_left(rb, ea);
-      Elim ec = make_elim(rc);
-      park(pc, T, tid, ec);
-      apply_right(rb, ec);
-      apply_left(rd, ec);
-    }
-    __syncthreads();
+    if (!jac) { redo = true; continue; }      // same iterate again, now with the Jacobian
+    redo = false;
+    // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------
     if (tid + 1 < T) {
       Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
       apply_right(rd, en);
@@ -504,14 +543,32 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       R[p] = rd.r[0]; R[T + p] = rd.r[1];
     }
     __syncthreads();
-    for (int l = 0; (T >> (l + 1)) > 0; ++l) {
-      const int ns = T >> (l + 1);
-      if (tid < ns) cr_forward(lay, l, tid, Lo, Dg, Up, R, T);
+    // Levels with more than 32 survivors use the whole CTA; the top of the
+    // reduction tree (<= 32 rows per level, forward and backward) is run by
+    // warp 0 alone with warp-level synchronisation, which replaces 2*log2(T)-9
+    // CTA barriers by one.
+    {
+      int l = 0;
+      for (; (T >> (l + 1)) > 32; ++l) {
+        if (tid < (T >> (l + 1))) cr_forward(lay, l, tid, Lo, Dg, Up, R, T);
+        __syncthreads();
+      }
+      const int l_warp = l;
+      if (tid < 32) {
+        for (; (T >> (l + 1)) > 0; ++l) {
+          if (tid < (T >> (l + 1))) cr_forward(lay, l, tid, Lo, Dg, Up, R, T);
+          __syncwarp();
+        }
+        for (l = lay.nlev - 1; l >= l_warp; --l) {
+          if (tid < lay.cnt[l]) cr_backward(lay, l, tid, Lo, Dg, Up, R, T);
+          __syncwarp();
+        }
+      }
       __syncthreads();
-    }
-    for (int l = lay.nlev - 1; l >= 0; --l) {
-      if (tid < lay.cnt[l]) cr_backward(lay, l, tid, Lo, Dg, Up, R, T);
-      __syncthreads();
+      for (l = l_warp - 1; l >= 0; --l) {
+        if (tid < lay.cnt[l]) cr_backward(lay, l, tid, Lo, Dg, Up, R, T);
+        __syncthreads();
+      }
     }
     // ---- back-substitution of the own vertices, U -= dU ----------------------
     {
@@ -913,6 +970,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   n->artery_threads = 32;
   while (4 * n->artery_threads < nd.np) n->artery_threads *= 2;
   n->artery_smem = (size_t)AF_ARTERY_SMEM_PER_THREAD * n->artery_threads * sizeof(double);
+  cr_layout_init(nd.lay, n->artery_threads);
   n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
   cudaError_t e;
   switch (n->artery_threads) {

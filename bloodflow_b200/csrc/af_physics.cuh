@@ -886,6 +886,7 @@ AF_HD void row_identity(Row& w) {
 // part of cell i (Gl, JA[0..1], Jq[0..1] in `own`).  sA/sq: the iterate U.
 // On the first pass (U == Un) the explicit part E of the residual is produced,
 // afterwards it is consumed.  Vertices i >= np are padding (identity rows).
+template <bool JAC>
 AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* sA, const double* sq,
                      const CellInt& left, const CellInt& own, double& EA, double& Eq, Row& row) {
   if (i >= c.np) {
@@ -896,8 +897,9 @@ AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* s
   const bool end = (i == 0 || i == ne);
   double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
   if (end) {
-    PointTerms ft = facet_terms<true>(i == 0 ? c.c1_0 : c.c1_L, sA[i], sq[i]);
-    fF2 = ft.F2; fdA = ft.dF2dA; fdq = ft.dF2dq;
+    PointTerms ft = facet_terms<JAC>(i == 0 ? c.c1_0 : c.c1_L, sA[i], sq[i]);
+    fF2 = ft.F2;
+    if (JAC) { fdA = ft.dF2dA; fdq = ft.dF2dq; }
   }
   VertexX vx = vertex_x(i, ne, c.h, i > 0 ? sA[i - 1] : 0.0, i > 0 ? sq[i - 1] : 0.0, sA[i], sq[i],
                         i < ne ? sA[i + 1] : 0.0, i < ne ? sq[i + 1] : 0.0, left.Gr, own.Gl, fF2);
@@ -907,9 +909,11 @@ AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* s
   }
   row.r[0] = vx.mA + c.dth * vx.XA + EA;
   row.r[1] = vx.mq + c.dth * vx.Xq + Eq;
-  VertexRow vr = vertex_jacobian(i, ne, c.h, c.dth, left.JA, left.Jq, own.JA, own.Jq, fdA, fdq);
+  if (JAC) {
+    VertexRow vr = vertex_jacobian(i, ne, c.h, c.dth, left.JA, left.Jq, own.JA, own.Jq, fdA, fdq);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { row.lo[k] = vr.lo[k]; row.dg[k] = vr.dg[k]; row.up[k] = vr.up[k]; }
+    for (int k = 0; k < 4; ++k) { row.lo[k] = vr.lo[k]; row.dg[k] = vr.dg[k]; row.up[k] = vr.up[k]; }
+  }
   if (end) {
     // [3P] DirichletBC rows: residual = U - g, Jacobian row = identity
     const bool fixA = (i == 0) ? !c.root : true;
