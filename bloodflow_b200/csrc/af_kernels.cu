@@ -54,7 +54,6 @@ struct NetDev {
   double newton_rtol, newton_atol;
   int newton_max_it, junction_k_max, picard_k_max;
   double junction_tol, picard_tol, cfl_margin;
-  CrLayout lay;          // level-blocked layout of the T-row reduced system of k_artery
   // per-step counter log
   int* log_art;
   int* log_j;
@@ -313,14 +312,14 @@ __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
 // Per Newton pass a thread (1) integrates its four cells, (2) builds its four
 // rows in registers, (3) after the residual test eliminates three of them in
 // registers (levels 0 and 1 of the cyclic reduction; the eliminated vertices
-// are parked in shared memory as x = g - P x_l - Q x_r), (4) hands one reduced
-// row to the level-blocked shared-memory reduction over T rows, and (5)
-// back-substitutes its own vertices.  Shared memory, in doubles (T threads):
-//   U(A,q) 8T | reduced Lo,Dg,Up,R 14T | parked a,b,c 30T   = 52T
-// i.e. 104 KB for the 1001-vertex arteries of the order-8 tree (T = 256), two
+// are parked in shared memory as x = g - P x_l - Q x_r), (4) solves the T-row
+// reduced system by parallel cyclic reduction with the row kept in registers,
+// and (5) back-substitutes its own vertices.  Shared memory, in doubles (T threads):
+//   U(A,q) 8T | PCR exchange 10T | parked a,b,c 30T   = 48T
+// i.e. 96 KB for the 1001-vertex arteries of the order-8 tree (T = 256), two
 // CTAs per SM, so all 255 arteries are co-resident.
 // ---------------------------------------------------------------------------
-#define AF_ARTERY_SMEM_PER_THREAD 52
+#define AF_ARTERY_SMEM_PER_THREAD 48
 
 template <int T>
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -441,17 +440,13 @@ __global__ void __launch_bounds__(T, (T <= 256 ? 512 / T : 1))
 k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   extern __shared__ double sm[];
   __shared__ double red[32];
-  const CrLayout& lay = nd.lay;
   constexpr int NV = 4 * T;
   const int np = nd.np, ne = nd.Nx, S = nd.S;
   const int tid = threadIdx.x;
   double* sA = sm;
   double* sq = sA + NV;
-  double* Lo = sq + NV;
-  double* Dg = Lo + 4 * T;
-  double* Up = Dg + 4 * T;
-  double* R = Up + 4 * T;
-  double* pa = R + 2 * T;     // parked vertex a (also the cell exchange buffer)
+  double* Lo = sq + NV;       // 10T: exchange buffer of the reduced-system PCR
+  double* pa = Lo + 10 * T;   // parked vertex a
   double* pb = pa + 10 * T;
   double* pc = pb + 10 * T;
 
@@ -528,57 +523,35 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       Elim en = unpark(pb, T, tid + 1);      // vertex b of the next thread
       apply_right(rd, en);
     }
-    // ---- the reduced system (one row per thread), level-blocked --------------
+    // ---- the reduced system (one row per thread): parallel cyclic reduction ---
+    // The row stays in registers.  In step s = 1, 2, 4, ... every thread turns
+    // its row into x_t = g - P x_{t-s} - Q x_{t+s}, publishes (P, Q, g) and
+    // eliminates both neighbours at distance s; after log2(T) steps the rows are
+    // decoupled.  All warps stay busy and there is no backward sweep: on this
+    // latency-bound kernel the shorter serial chain beats the work-optimal
+    // cyclic reduction (profiles/README.md).
+    double xd[2], xl[2] = {0.0, 0.0};
     {
-      const int p = cr_pos(lay, tid);
-      if ((tid & 1) == 0) {
-        double di[4];
-        inv2v(rd.dg, di);
-        st2(Dg, T, p, di);
-      } else {
-        st2(Dg, T, p, rd.dg);
-      }
-      st2(Lo, T, p, rd.lo);
-      st2(Up, T, p, rd.up);
-      R[p] = rd.r[0]; R[T + p] = rd.r[1];
-    }
-    __syncthreads();
-    // Levels with more than 32 survivors use the whole CTA; the top of the
-    // reduction tree (<= 32 rows per level, forward and backward) is run by
-    // warp 0 alone with warp-level synchronisation, which replaces 2*log2(T)-9
-    // CTA barriers by one.
-    {
-      int l = 0;
-      for (; (T >> (l + 1)) > 32; ++l) {
-        if (tid < (T >> (l + 1))) cr_forward(lay, l, tid, Lo, Dg, Up, R, T);
+      double* buf = Lo;                       // 10T doubles of the 14T scratch
+#pragma unroll 1
+      for (int sdist = 1; sdist < T; sdist *= 2) {
+        park(buf, T, tid, make_elim(rd));
+        __syncthreads();
+        if (tid >= sdist) apply_left(rd, unpark(buf, T, tid - sdist));
+        if (tid + sdist < T) apply_right(rd, unpark(buf, T, tid + sdist));
         __syncthreads();
       }
-      const int l_warp = l;
-      if (tid < 32) {
-        for (; (T >> (l + 1)) > 0; ++l) {
-          if (tid < (T >> (l + 1))) cr_forward(lay, l, tid, Lo, Dg, Up, R, T);
-          __syncwarp();
-        }
-        for (l = lay.nlev - 1; l >= l_warp; --l) {
-          if (tid < lay.cnt[l]) cr_backward(lay, l, tid, Lo, Dg, Up, R, T);
-          __syncwarp();
-        }
-      }
+      double inv[4];
+      inv2v(rd.dg, inv);
+      xd[0] = inv[0] * rd.r[0] + inv[1] * rd.r[1];
+      xd[1] = inv[2] * rd.r[0] + inv[3] * rd.r[1];
+      buf[tid] = xd[0]; buf[T + tid] = xd[1];
       __syncthreads();
-      for (l = l_warp - 1; l >= 0; --l) {
-        if (tid < lay.cnt[l]) cr_backward(lay, l, tid, Lo, Dg, Up, R, T);
-        __syncthreads();
-      }
+      if (tid > 0) { xl[0] = buf[tid - 1]; xl[1] = buf[T + tid - 1]; }
     }
     // ---- back-substitution of the own vertices, U -= dU ----------------------
     {
-      double xl[2] = {0.0, 0.0}, xd[2], xa[2], xb[2], xc[2];
-      const int p = cr_pos(lay, tid);
-      xd[0] = R[p]; xd[1] = R[T + p];
-      if (tid > 0) {
-        const int pl = cr_pos(lay, tid - 1);
-        xl[0] = R[pl]; xl[1] = R[T + pl];
-      }
+      double xa[2], xb[2], xc[2];
       back_sub(unpark(pb, T, tid), xl, xd, xb);
       back_sub(unpark(pa, T, tid), xl, xb, xa);
       back_sub(unpark(pc, T, tid), xb, xd, xc);
@@ -970,7 +943,6 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   n->artery_threads = 32;
   while (4 * n->artery_threads < nd.np) n->artery_threads *= 2;
   n->artery_smem = (size_t)AF_ARTERY_SMEM_PER_THREAD * n->artery_threads * sizeof(double);
-  cr_layout_init(nd.lay, n->artery_threads);
   n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
   cudaError_t e;
   switch (n->artery_threads) {

@@ -999,135 +999,4 @@ AF_HD void back_sub(const Elim& e, const double xl[2], const double xr[2], doubl
   x[1] = e.g[1] - (e.P[2] * xl[0] + e.P[3] * xl[1]) - (e.Q[2] * xr[0] + e.Q[3] * xr[1]);
 }
 
-// ---------------------------------------------------------------------------
-// 2x2-block tridiagonal solve: block cyclic reduction on a LEVEL-BLOCKED
-// layout.  Vertex i is eliminated at level l = ctz(i+1); all vertices of one
-// level are stored contiguously (block l, index (i+1) >> (l+1)), so every
-// level of the reduction reads and writes unit-stride shared memory.  Rows
-// that are about to be eliminated hold the INVERSE of their diagonal block.
-// Arrays are component-major: blk[c*ld + pos], c = 0..3 (row-major 2x2).
-// ---------------------------------------------------------------------------
-struct CrLayout {
-  int n, nlev;
-  int off[14], cnt[14];
-};
-
-AF_HD int af_ctz(int x) {
-#ifdef __CUDA_ARCH__
-  return __ffs(x) - 1;
-#else
-  return __builtin_ctz((unsigned)x);
-#endif
-}
-
-AF_HD void cr_layout_init(CrLayout& L, int n) {
-  L.n = n;
-  int off = 0, l = 0;
-  for (; l < 14; ++l) {
-    int c = (n + (1 << l)) >> (l + 1);
-    if (c == 0) break;
-    L.off[l] = off; L.cnt[l] = c;
-    off += c;
-  }
-  L.nlev = l;
-}
-
-AF_HD int cr_pos(const CrLayout& L, int i) {
-  int l = af_ctz(i + 1);
-  return L.off[l] + ((i + 1) >> (l + 1));
-}
-
-AF_HD void ld2(const double* m, int ld, int i, double o[4]) {
-  o[0] = m[i]; o[1] = m[ld + i]; o[2] = m[2 * ld + i]; o[3] = m[3 * ld + i];
-}
-
-AF_HD void st2(double* m, int ld, int i, const double o[4]) {
-  m[i] = o[0]; m[ld + i] = o[1]; m[2 * ld + i] = o[2]; m[3 * ld + i] = o[3];
-}
-
-// Forward step of level l for survivor m (vertex i = 2s(m+1)-1, s = 2^l):
-// eliminate its neighbours i-s, i+s (block l entries m, m+1, which hold inverse
-// diagonals).  If the survivor is eliminated at level l+1 its new diagonal is
-// stored inverted.
-AF_HD void cr_forward(const CrLayout& L, int l, int m, double* Lo, double* Dg, double* Up, double* R, int ld) {
-  const int s = 1 << l;
-  const int i = 2 * s * (m + 1) - 1;
-  const int pi = cr_pos(L, i);
-  const int pj = L.off[l] + m;
-  double d[4], lo[4], up[4] = {0.0, 0.0, 0.0, 0.0};
-  ld2(Dg, ld, pi, d);
-  double r0 = R[pi], r1 = R[ld + pi];
-  {
-    double inv[4], t[4], al[4], mm[4];
-    ld2(Dg, ld, pj, inv);
-    ld2(Lo, ld, pi, t);
-    mul2(t, inv, al);                 // al = Lo_i * D_j^-1
-    ld2(Up, ld, pj, t);
-    mul2(al, t, mm);
-    d[0] -= mm[0]; d[1] -= mm[1]; d[2] -= mm[2]; d[3] -= mm[3];
-    double rj0 = R[pj], rj1 = R[ld + pj];
-    r0 -= al[0] * rj0 + al[1] * rj1;
-    r1 -= al[2] * rj0 + al[3] * rj1;
-    ld2(Lo, ld, pj, t);
-    mul2(al, t, mm);
-    lo[0] = -mm[0]; lo[1] = -mm[1]; lo[2] = -mm[2]; lo[3] = -mm[3];
-  }
-  if (m + 1 < L.cnt[l]) {             // vertex i+s exists
-    const int pk = pj + 1;
-    double inv[4], t[4], ga[4], mm[4];
-    ld2(Dg, ld, pk, inv);
-    ld2(Up, ld, pi, t);
-    mul2(t, inv, ga);                 // ga = Up_i * D_k^-1
-    ld2(Lo, ld, pk, t);
-    mul2(ga, t, mm);
-    d[0] -= mm[0]; d[1] -= mm[1]; d[2] -= mm[2]; d[3] -= mm[3];
-    double rk0 = R[pk], rk1 = R[ld + pk];
-    r0 -= ga[0] * rk0 + ga[1] * rk1;
-    r1 -= ga[2] * rk0 + ga[3] * rk1;
-    ld2(Up, ld, pk, t);
-    mul2(ga, t, mm);
-    up[0] = -mm[0]; up[1] = -mm[1]; up[2] = -mm[2]; up[3] = -mm[3];
-  }
-  if ((m + 1) & 1) {                  // eliminated at level l+1: keep the inverse
-    double di[4];
-    inv2v(d, di);
-    st2(Dg, ld, pi, di);
-  } else {
-    st2(Dg, ld, pi, d);
-  }
-  st2(Lo, ld, pi, lo);
-  st2(Up, ld, pi, up);
-  R[pi] = r0; R[ld + pi] = r1;
-}
-
-// Back-substitution of level l for block entry k (vertex i = (2k+1)s - 1):
-// x_i = D_i^-1 (R_i - Lo_i x_{i-s} - Up_i x_{i+s}); the solution overwrites R.
-AF_HD void cr_backward(const CrLayout& L, int l, int k, const double* Lo, const double* Dg, const double* Up,
-                       double* R, int ld) {
-  const int s = 1 << l;
-  const int i = (2 * k + 1) * s - 1;
-  const int pi = L.off[l] + k;
-  double r0 = R[pi], r1 = R[ld + pi];
-  if (k > 0) {
-    const int pj = cr_pos(L, i - s);
-    double t[4];
-    ld2(Lo, ld, pi, t);
-    double x0 = R[pj], x1 = R[ld + pj];
-    r0 -= t[0] * x0 + t[1] * x1;
-    r1 -= t[2] * x0 + t[3] * x1;
-  }
-  if (i + s < L.n) {
-    const int pj = cr_pos(L, i + s);
-    double t[4];
-    ld2(Up, ld, pi, t);
-    double x0 = R[pj], x1 = R[ld + pj];
-    r0 -= t[0] * x0 + t[1] * x1;
-    r1 -= t[2] * x0 + t[3] * x1;
-  }
-  double inv[4];
-  ld2(Dg, ld, pi, inv);
-  R[pi] = inv[0] * r0 + inv[1] * r1;
-  R[ld + pi] = inv[2] * r0 + inv[3] * r1;
-}
-
 }  // namespace af

@@ -121,11 +121,8 @@ int hh_artery_solve(const double* vp, int Nx, double dt, double theta, double* A
   const int NV = 4 * T;
   std::vector<double> sA(NV, 1.0), sq(NV, 0.0), EA(NV), Eq(NV);
   for (int i = 0; i < np; ++i) { sA[i] = A[i]; sq[i] = q[i]; }
-  std::vector<double> Lo(4 * T), Dg(4 * T), Up(4 * T), R(2 * T);
   std::vector<Row> rows(NV);
   std::vector<Elim> ea(T), eb(T), ec(T);
-  CrLayout lay;
-  cr_layout_init(lay, T);
   ArteryCtx c;
   c.ne = ne; c.np = np; c.h = v.dx; c.Kr = -v.src_k; c.dth = dt * theta; c.dte = dt * (1.0 - theta);
   c.c1_0 = v.f0 * sqrt(v.A00); c.c1_L = v.fL * sqrt(v.A0L);
@@ -185,25 +182,29 @@ int hh_artery_solve(const double* vp, int Nx, double dt, double theta, double* A
       eb[t] = make_elim(rb);
       apply_left(rd, eb[t]);
     }
-    for (int t = 0; t < T; ++t) {          // level 1 across threads, reduced row
-      Row& rd = rows[4 * t + 3];
-      if (t + 1 < T) apply_right(rd, eb[t + 1]);
-      const int p = cr_pos(lay, t);
-      if ((t & 1) == 0) { double di[4]; inv2v(rd.dg, di); st2(Dg.data(), T, p, di); }
-      else st2(Dg.data(), T, p, rd.dg);
-      st2(Lo.data(), T, p, rd.lo);
-      st2(Up.data(), T, p, rd.up);
-      R[p] = rd.r[0]; R[T + p] = rd.r[1];
+    for (int t = 0; t < T; ++t)            // level 1 across threads
+      if (t + 1 < T) apply_right(rows[4 * t + 3], eb[t + 1]);
+    // reduced system: parallel cyclic reduction, one row per "thread"
+    std::vector<Elim> buf(T);
+    for (int sdist = 1; sdist < T; sdist *= 2) {
+      for (int t = 0; t < T; ++t) buf[t] = make_elim(rows[4 * t + 3]);
+      for (int t = 0; t < T; ++t) {
+        Row& rd = rows[4 * t + 3];
+        if (t >= sdist) apply_left(rd, buf[t - sdist]);
+        if (t + sdist < T) apply_right(rd, buf[t + sdist]);
+      }
     }
-    for (int l = 0; (T >> (l + 1)) > 0; ++l)
-      for (int m = 0; m < (T >> (l + 1)); ++m) cr_forward(lay, l, m, Lo.data(), Dg.data(), Up.data(), R.data(), T);
-    for (int l = lay.nlev - 1; l >= 0; --l)
-      for (int k = 0; k < lay.cnt[l]; ++k) cr_backward(lay, l, k, Lo.data(), Dg.data(), Up.data(), R.data(), T);
+    std::vector<double> X(2 * T);
     for (int t = 0; t < T; ++t) {
-      double xl[2] = {0.0, 0.0}, xd[2], xa[2], xb[2], xc[2];
-      const int p = cr_pos(lay, t);
-      xd[0] = R[p]; xd[1] = R[T + p];
-      if (t > 0) { const int pl = cr_pos(lay, t - 1); xl[0] = R[pl]; xl[1] = R[T + pl]; }
+      const Row& rd = rows[4 * t + 3];
+      double inv[4];
+      inv2v(rd.dg, inv);
+      X[t] = inv[0] * rd.r[0] + inv[1] * rd.r[1];
+      X[T + t] = inv[2] * rd.r[0] + inv[3] * rd.r[1];
+    }
+    for (int t = 0; t < T; ++t) {
+      double xl[2] = {0.0, 0.0}, xd[2] = {X[t], X[T + t]}, xa[2], xb[2], xc[2];
+      if (t > 0) { xl[0] = X[t - 1]; xl[1] = X[T + t - 1]; }
       back_sub(eb[t], xl, xd, xb);
       back_sub(ea[t], xl, xb, xa);
       back_sub(ec[t], xb, xd, xc);
