@@ -282,6 +282,58 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
   if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)AF_FLAG_PICARD_KMAX);
 }
 
+// one warp per leaf (single networks): lanes 0..2 take the three stencil points
+// L-2dex, L-dex, L of windkessel() (an:383-390), lanes 0..1 the two half steps
+// (an:393-398); the Picard loop is inherently serial.
+__device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b, int l, int log_slot) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int k = lane % 3;
+  const int ba = b * nd.na + nd.leaf_art[l];
+  const size_t off = (size_t)ba * nd.S;
+  const double* A = nd.A[cur] + off;
+  const double* q = nd.q[cur] + off;
+  const Vessel ves = nd.ves[ba];
+  const double L = ves.L, dt = nd.dt;
+  // adjust_dex (ar:349-365)
+  Coef cL;
+  cL.f = ves.fL; cL.A0 = ves.A0L;
+  double AL, qL;
+  interp_state(A, q, nd.Nx, ves.dx, L, AL, qL);
+  const double dex = (1.0 + nd.cfl_margin) * dt / cfl_term(ves, cL, AL, qL);
+  // stencil point of this lane and its flux / source (an:385-390)
+  const double xk = L - (double)(2 - k) * dex;
+  double Ak, qk;
+  interp_state(A, q, nd.Nx, ves.dx, xk, Ak, qk);
+  const Coef ck = coef_at(ves, xk);
+  const double Fk = bc_flux2(ck, Ak, qk), Sk = bc_source2(ves, ck, Ak, qk);
+  // half step between this point and the next one (compute_U_half, an:393-394)
+  const double xn = __shfl_down_sync(FULL, xk, 1), An = __shfl_down_sync(FULL, Ak, 1);
+  const double qn = __shfl_down_sync(FULL, qk, 1), Fn = __shfl_down_sync(FULL, Fk, 1);
+  const double Sn = __shfl_down_sync(FULL, Sk, 1);
+  const double rr = dt / (xn - xk);
+  const double Ah = (Ak + An) / 2.0 - rr * (qn - qk);
+  const double qh = (qk + qn) / 2.0 - rr * (Fn - Fk) + dt / 4.0 * (Sk + Sn);
+  const double xh = L - (1.5 - (double)k) * dex;       // L-1.5dex, L-0.5dex
+  const Coef ch = coef_at(ves, xh);
+  const double Fh = bc_flux2(ch, Ah, qh), Sh = bc_source2(ves, ch, Ah, qh);
+  // value at t_(n+1) in L-dex (an:401-403)
+  const double F21 = __shfl_sync(FULL, Fh, 0), S21 = __shfl_sync(FULL, Sh, 0);
+  const double F10 = __shfl_sync(FULL, Fh, 1), S10 = __shfl_sync(FULL, Sh, 1);
+  const double q1 = __shfl_sync(FULL, qk, 1);
+  const double A0s = __shfl_sync(FULL, Ak, 2), q0s = __shfl_sync(FULL, qk, 2);
+  const double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
+  if (lane != 0) return;
+  const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
+  WkResult r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
+  nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
+  nd.dex[ba] = r.dex;
+  nd.picard_its[b * nd.nl + l] = r.its;
+  if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
+  atomicAdd(&nd.totals[2], (unsigned long long)r.its);
+  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)AF_FLAG_PICARD_KMAX);
+}
+
 __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
@@ -290,9 +342,9 @@ __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
     long long task = gt >> 5;
     if (task < n_j) {
       junction_task_warp(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
-    } else if (task < n_j + n_l && (threadIdx.x & 31) == 0) {
+    } else if (task < n_j + n_l) {
       task -= n_j;
-      leaf_task(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+      leaf_task_warp(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
     }
     return;
   }

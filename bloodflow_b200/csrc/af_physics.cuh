@@ -143,28 +143,11 @@ struct WkResult {
   int its;
 };
 
-AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int Nx, double dt, double R1,
-                          double R2, double CT, int k_max, double tol, double margin) {
+// The Picard iteration of an:405-422 given the outlet state (A0s, q0s) = Un(L),
+// the Lax-Wendroff value qm1 at L-dex and the step dex.
+AF_HD WkResult windkessel_picard(const Vessel& v, double dt, double dex, double A0s, double q0s, double qm1,
+                                 double R1, double R2, double CT, int k_max, double tol) {
   WkResult r;
-  double L = v.L;
-  Coef cL;
-  cL.f = v.fL; cL.A0 = v.A0L;
-  double AL, qL;
-  interp_state(A, q, Nx, v.dx, L, AL, qL);
-  double dex = (1.0 + margin) * dt / cfl_term(v, cL, AL, qL);       // adjust_dex (ar:349-365)
-  double x2 = L - 2.0 * dex, x1 = L - dex, x0 = L;
-  double x21 = L - 1.5 * dex, x10 = L - 0.5 * dex;
-  double A2, q2, A1, q1, A0s, q0s;
-  interp_state(A, q, Nx, v.dx, x2, A2, q2);
-  interp_state(A, q, Nx, v.dx, x1, A1, q1);
-  interp_state(A, q, Nx, v.dx, x0, A0s, q0s);
-  double Ah21, qh21, Ah10, qh10;
-  u_half(v, dt, x2, x1, A2, q2, A1, q1, Ah21, qh21);
-  u_half(v, dt, x1, x0, A1, q1, A0s, q0s, Ah10, qh10);
-  Coef c21 = coef_at(v, x21), c10 = coef_at(v, x10);
-  double F21 = bc_flux2(c21, Ah21, qh21), S21 = bc_source2(v, c21, Ah21, qh21);
-  double F10 = bc_flux2(c10, Ah10, qh10), S10 = bc_source2(v, c10, Ah10, qh10);
-  double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
   double pn = outlet_pressure(v, A0s);
   // Fixed-point map of an:411-420,
   //   qm0 = q + (p-pn)/R1 + dt/(R1 R2 C) pn - dt (R1+R2)/(R1 R2 C) q,
@@ -209,6 +192,31 @@ AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int
   r.its = k;
   return r;
 }
+
+AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int Nx, double dt, double R1,
+                          double R2, double CT, int k_max, double tol, double margin) {
+  double L = v.L;
+  Coef cL;
+  cL.f = v.fL; cL.A0 = v.A0L;
+  double AL, qL;
+  interp_state(A, q, Nx, v.dx, L, AL, qL);
+  double dex = (1.0 + margin) * dt / cfl_term(v, cL, AL, qL);       // adjust_dex (ar:349-365)
+  double x2 = L - 2.0 * dex, x1 = L - dex, x0 = L;
+  double x21 = L - 1.5 * dex, x10 = L - 0.5 * dex;
+  double A2, q2, A1, q1, A0s, q0s;
+  interp_state(A, q, Nx, v.dx, x2, A2, q2);
+  interp_state(A, q, Nx, v.dx, x1, A1, q1);
+  interp_state(A, q, Nx, v.dx, x0, A0s, q0s);
+  double Ah21, qh21, Ah10, qh10;
+  u_half(v, dt, x2, x1, A2, q2, A1, q1, Ah21, qh21);
+  u_half(v, dt, x1, x0, A1, q1, A0s, q0s, Ah10, qh10);
+  Coef c21 = coef_at(v, x21), c10 = coef_at(v, x10);
+  double F21 = bc_flux2(c21, Ah21, qh21), S21 = bc_source2(v, c21, Ah21, qh21);
+  double F10 = bc_flux2(c10, Ah10, qh10), S10 = bc_source2(v, c10, Ah10, qh10);
+  double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
+  return windkessel_picard(v, dt, dex, A0s, q0s, qm1, R1, R2, CT, k_max, tol);
+}
+
 
 // ---------------------------------------------------------------------------
 // Bifurcation: 18 unknowns (an:476-710).  Unknown layout per vessel v
@@ -402,6 +410,22 @@ AF_HD int solve3(double M[9], double b[3]) {
   return 0;
 }
 
+// "Arrow" 3x3 system  [d0 d1 d2; m1 e1 0; m2 0 e2] x = b  (one dense row, two
+// rows with two entries): eliminate x1, x2 through their own rows.  The two
+// reciprocals are independent, so the serial chain is two divisions long.
+// Returns 1 if a pivot vanishes.
+AF_HD int solve_arrow3(double d0, double d1, double d2, double m1, double e1, double m2, double e2, double b[3]) {
+  if (e1 == 0.0 || e2 == 0.0) return 1;
+  const double i1 = 1.0 / e1, i2 = 1.0 / e2;
+  const double den = d0 - d1 * (m1 * i1) - d2 * (m2 * i2);
+  if (den == 0.0) return 1;
+  const double x0 = (b[0] - d1 * (b[1] * i1) - d2 * (b[2] * i2)) / den;
+  b[1] = (b[1] - m1 * x0) * i1;
+  b[2] = (b[2] - m2 * x0) * i2;
+  b[0] = x0;
+  return 0;
+}
+
 // One Newton iteration's data: residual y[18] and the 15 state-dependent
 // Jacobian entries (the other 26 non-zeros are the constants 2, -1, +-1 and
 // +-dt/dex).  Same formulas as junction_residual/junction_jacobian.
@@ -456,35 +480,24 @@ AF_HD int junction_solve_structured(const JunctionCtx& c, const JunctionLin& l, 
   const double sig[3] = {1.0, -1.0, -1.0};
   // J[15+v, qg_v] = s*dt/dex (row 17 with d1's ratio, an:662)
   const double cq[3] = {c.dtdex[0], -c.dtdex[1], -c.dtdex[1]};
-  double M[9], b[3];
-  M[0] = 0.5; M[1] = -0.5; M[2] = -0.5;
+  double b[3];
+  // rows 7, 10, 11 -> dqg
   b[0] = y[7] - (y[0] - y[1] - y[2]) / 2.0;
-#pragma unroll
-  for (int k = 1; k < 3; ++k) {
-    double a0 = l.dPf[0], ak = -l.dPf[k];
-    M[k * 3 + 0] = -a0 * cq[0];
-    M[k * 3 + 1] = k == 1 ? -ak * cq[1] : 0.0;
-    M[k * 3 + 2] = k == 2 ? -ak * cq[2] : 0.0;
-    b[k] = y[9 + k] - a0 * y[15] - ak * y[15 + k];
-  }
-  if (solve3(M, b)) return 1;
+  b[1] = y[10] - l.dPf[0] * y[15] + l.dPf[1] * y[16];
+  b[2] = y[11] - l.dPf[0] * y[15] + l.dPf[2] * y[17];
+  if (solve_arrow3(0.5, -0.5, -0.5, -l.dPf[0] * cq[0], l.dPf[1] * cq[1], -l.dPf[0] * cq[0], l.dPf[2] * cq[2], b))
+    return 1;
   double dqg[3] = {b[0], b[1], b[2]};
-#pragma unroll
-  for (int k = 1; k < 3; ++k) {
-    double a0 = l.dPh[0], ak = -l.dPh[k];
-    M[(k - 1) * 3 + 0] = a0 / 2.0;
-    M[(k - 1) * 3 + 1] = k == 1 ? ak / 2.0 : 0.0;
-    M[(k - 1) * 3 + 2] = k == 2 ? ak / 2.0 : 0.0;
-    b[k - 1] = y[7 + k] - a0 * y[3] / 2.0 - ak * y[3 + k] / 2.0;
-  }
+  // rows 6, 8, 9 -> dAg
   double acc = 0.0;
 #pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    M[6 + v] = -sig[v] * l.gA[v];
-    acc += sig[v] * (y[12 + v] - l.gq[v] * dqg[v]);
-  }
-  b[2] = y[6] - acc;
-  if (solve3(M, b)) return 1;
+  for (int v = 0; v < 3; ++v) acc += sig[v] * (y[12 + v] - l.gq[v] * dqg[v]);
+  b[0] = y[6] - acc;
+  b[1] = y[8] - l.dPh[0] * y[3] / 2.0 + l.dPh[1] * y[4] / 2.0;
+  b[2] = y[9] - l.dPh[0] * y[3] / 2.0 + l.dPh[2] * y[5] / 2.0;
+  if (solve_arrow3(-sig[0] * l.gA[0], -sig[1] * l.gA[1], -sig[2] * l.gA[2], l.dPh[0] / 2.0, -l.dPh[1] / 2.0,
+                   l.dPh[0] / 2.0, -l.dPh[2] / 2.0, b))
+    return 1;
   double d[18];
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
