@@ -39,7 +39,7 @@ class AfDesc(ctypes.Structure):
         ('q_ins', P_dbl),
         ('newton_rtol', c_dbl), ('newton_atol', c_dbl), ('newton_max_it', c_i32), ('junction_k_max', c_i32),
         ('junction_tol', c_dbl), ('picard_k_max', c_i32), ('picard_tol', c_dbl), ('cfl_margin', c_dbl),
-        ('device', c_i32), ('reserved', c_i32), ('stream', ctypes.c_void_p),
+        ('device', c_i32), ('root_artery', c_i32), ('stream', ctypes.c_void_p),
     ]
 
 

@@ -119,7 +119,8 @@ class Artery(object):
             self.Nx, self.Nt, self.theta, self.dt, junctions=np.zeros((0, 3)), leaves=[0] if self.leaf else [],
             k1=p['k1'], k2=p['k2'], k3=p['k3'], rho=p['rho'], Re=p['Re'], db=self.db, p0=p['p0'],
             Ru=[[self._Ru]], Rd=[[self._Rd]], L=[[self._L]], q0=[[self.q0]],
-            R1=wk[0] * 0.3, R2=wk[1] * 0.01, CT=wk[2], q_ins=np.full(self.Nt, self.q0))
+            R1=wk[0] * 0.3, R2=wk[1] * 0.01, CT=wk[2], q_ins=np.full(self.Nt, self.q0),
+            root_artery=0 if self.root else -1)
         self._k, self._b, self._own = 0, 0, True
 
     def _attach(self, dev, k, b=0):

@@ -11,6 +11,7 @@
 // k_artery (one CTA per artery) make a time step; see DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,6 +29,7 @@ using namespace af;
 // ---------------------------------------------------------------------------
 struct NetDev {
   int nb, na, nj, nl, Nx, np, S, Nt;
+  int root_artery;
   double dt, theta;
   const int* j_p;
   const int* j_d1;
@@ -520,7 +522,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   c.h = v.dx; c.Kr = -v.src_k;
   c.dth = nd.dt * nd.theta; c.dte = nd.dt * (1.0 - nd.theta);
   c.c1_0 = v.f0 * sqrt(v.A00); c.c1_L = v.fL * sqrt(v.A0L);
-  c.root = (a == 0); c.leaf = nd.art_leaf[a] >= 0;
+  c.root = (a == nd.root_artery); c.leaf = nd.art_leaf[a] >= 0;
   // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
   c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
   c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
@@ -814,6 +816,7 @@ struct af_net {
   int artery_threads = 256;
   size_t artery_smem = 0;
   int boundary_lanes = 32;
+  int boundary_block = 64;         // threads per CTA of k_boundary (AF_BOUNDARY_BLOCK overrides)
   std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
   int n_pending = 0;
 
@@ -877,7 +880,7 @@ static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_ind
 static cudaError_t run_boundary(const af_net* n, int log_slot) {
   long long tasks = (long long)n->nd.nb * (n->nd.nj + n->nd.nl);
   long long threads = tasks * n->boundary_lanes;
-  int block = n->boundary_lanes == 32 ? 32 : 64;
+  int block = n->boundary_block;
   long long grid = (threads + block - 1) / block;
   if (grid == 0) return cudaSuccess;
   k_boundary<<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, n->boundary_lanes, log_slot);
@@ -920,6 +923,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   nd.junction_k_max = d->junction_k_max; nd.junction_tol = d->junction_tol;
   nd.picard_k_max = d->picard_k_max; nd.picard_tol = d->picard_tol; nd.cfl_margin = d->cfl_margin;
   nd.q_ins_per_net = d->q_ins_per_network;
+  nd.root_artery = d->root_artery;
 
   const size_t nba = (size_t)nd.nb * nd.na;
   int rc = AF_OK;
@@ -996,6 +1000,8 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   while (4 * n->artery_threads < nd.np) n->artery_threads *= 2;
   n->artery_smem = (size_t)AF_ARTERY_SMEM_PER_THREAD * n->artery_threads * sizeof(double);
   n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
+  n->boundary_block = 64;
+  if (const char* env = getenv("AF_BOUNDARY_BLOCK")) n->boundary_block = atoi(env);
   cudaError_t e;
   switch (n->artery_threads) {
     case 32: e = prepare_artery<32>(n); break;

@@ -14,7 +14,7 @@ from ._ffi import check, dptr, f64, i32, iptr, lib
 
 class DeviceNetwork(object):
     def __init__(self, Nx, Nt, theta, dt, junctions, leaves, k1, k2, k3, rho, Re, db, p0, Ru, Rd, L, q0,
-                 R1, R2, CT, q_ins, device=0, stream=None, **constants):
+                 R1, R2, CT, q_ins, device=0, stream=None, root_artery=0, **constants):
         Ru = np.atleast_2d(f64(Ru))
         self.nb, self.na = Ru.shape
         junctions = i32(junctions).reshape(-1, 3)
@@ -57,6 +57,7 @@ class DeviceNetwork(object):
                 raise TypeError("unknown solver constant %r" % name)
             setattr(d, name, value)
         d.device = int(device)
+        d.root_artery = int(root_artery)
         d.stream = stream
         self._h = _ffi.Handle()
         check(lib.af_net_create(ctypes.byref(d), ctypes.byref(self._h)))

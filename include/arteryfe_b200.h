@@ -67,7 +67,7 @@ typedef struct af_desc {
   double theta;         /* sol['theta'] */
   double dt;            /* T/Nt (an:83) */
 
-  /* topology, shared by the batch; artery 0 is the root */
+  /* topology, shared by the batch; artery `root_artery` (0) is the root */
   const int32_t* junction_parent; /* [n_junctions] compact artery index */
   const int32_t* junction_d1;
   const int32_t* junction_d2;
@@ -107,7 +107,8 @@ typedef struct af_desc {
   double cfl_margin;       /* 0.05  (an:713, ar:349) */
 
   int32_t device;          /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t root_artery;     /* compact index of the root (inlet: q only, ar:172-174); 0 by default,
+                              -1: no root, every inlet takes (A, q) (a stand-alone non-root Artery) */
   void* stream;            /* cudaStream_t to enqueue on, or NULL for an own stream */
 } af_desc;
 
