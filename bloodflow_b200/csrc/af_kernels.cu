@@ -41,7 +41,11 @@ struct NetDev {
   double* q[2];
   double* bc;
   double* dex;
-  double* jx;
+  double* jx;            // [nb*nj*18] junction unknowns (warm start), current
+  double* jx_next;       // second buffer: written by the fused step kernel, then swapped
+  const int* art_jin;    // [na] junction in which the artery is a daughter (-1: root)
+  const int* art_role;   // [na] 1 / 2: first / second daughter of art_jin
+  const int* art_jout;   // [na] junction of which the artery is the parent (-1: leaf)
   const double* wk;      // [nb*nl*3]  R1, R2, CT
   const double* q_ins;
   int q_ins_per_net;
@@ -210,7 +214,9 @@ __device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, 
 
 // one warp per junction (single networks): lane v < 3 owns vessel v; the 3x3
 // solves are done redundantly by every lane, so no result has to travel back.
-__device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, int log_slot) {
+// On return every lane holds x; dex, solves, fl are warp-uniform.
+__device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, int b, int j, const double* xg,
+                                                    double* x, double& dex, int& solves, uint32_t& fl) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v = lane % 3;
@@ -227,15 +233,14 @@ __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, in
     M = 1.0e300;
     M = m0 < M ? m0 : M; M = m1 < M ? m1 : M; M = m2 < M ? m2 : M;
   }
-  const double dex = (1.0 + nd.cfl_margin) * nd.dt / M;
+  dex = (1.0 + nd.cfl_margin) * nd.dt / M;
   JVessel jv;
   jvessel_prepare(jv, v, ves, A, q, nd.Nx, nd.dt, dex);
   const double dtdex_p = __shfl_sync(FULL, jv.dtdex, 0), dtdex_d1 = __shfl_sync(FULL, jv.dtdex, 1);
-  double x[18], x0[18];
-  const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
-  for (int i = 0; i < 18; ++i) x0[i] = x[i] = xg[i];
-  uint32_t fl = 0;
-  int solves = 0, k = 0;
+  for (int i = 0; i < 18; ++i) x[i] = xg[i];
+  fl = 0;
+  solves = 0;
+  int k = 0;
   bool singular = false;
   for (; k < nd.junction_k_max; ++k) {
     const double xv[6] = {x[3 * v], x[3 * v + 1], x[3 * v + 2], x[9 + 3 * v], x[10 + 3 * v], x[11 + 3 * v]};
@@ -260,13 +265,22 @@ __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, in
     for (int i = 0; i < 18; ++i) x[i] -= y[i];
     ++solves;
   }
-  if (lane != 0) return;
   if (k == nd.junction_k_max) fl |= AF_FLAG_JUNCTION_KMAX;
-  if (singular) {
-    for (int i = 0; i < 18; ++i) x[i] = x0[i];
+  if (singular) {               // warp-uniform; the verbatim dense path owns the reference's singular branch
+    for (int i = 0; i < 18; ++i) x[i] = xg[i];
     fl = 0;
     solves = junction_slow_path(nd, cur, b, ia, dex, x, &fl);
   }
+}
+
+__device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, int log_slot) {
+  double x[18], dex;
+  int solves;
+  uint32_t fl;
+  const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
+  junction_solve_warp(nd, cur, b, j, xg, x, dex, solves, fl);
+  if ((threadIdx.x & 31) != 0) return;
+  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
   junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot);
 }
 
@@ -287,7 +301,7 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
 // one warp per leaf (single networks): lanes 0..2 take the three stencil points
 // L-2dex, L-dex, L of windkessel() (an:383-390), lanes 0..1 the two half steps
 // (an:393-398); the Picard loop is inherently serial.
-__device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b, int l, int log_slot) {
+__device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, int b, int l, int log_slot) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = lane % 3;
@@ -325,15 +339,22 @@ __device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b,
   const double q1 = __shfl_sync(FULL, qk, 1);
   const double A0s = __shfl_sync(FULL, Ak, 2), q0s = __shfl_sync(FULL, qk, 2);
   const double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
-  if (lane != 0) return;
+  WkResult r;
+  r.A_out = 0.0; r.dex = dex; r.its = 0;
+  if (lane != 0) return r;
   const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
-  WkResult r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
+  r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
   nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
   nd.dex[ba] = r.dex;
   nd.picard_its[b * nd.nl + l] = r.its;
   if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
   atomicAdd(&nd.totals[2], (unsigned long long)r.its);
   if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)AF_FLAG_PICARD_KMAX);
+  return r;
+}
+
+__device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b, int l, int log_slot) {
+  leaf_solve_warp(nd, cur, b, l, log_slot);
 }
 
 __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
@@ -489,11 +510,12 @@ __device__ __forceinline__ double assemble_pass(const ArteryCtx& c, const CellCo
   return part;
 }
 
-template <int T>
+template <int T, bool FUSED>
 __global__ void __launch_bounds__(T, (T <= 256 ? 512 / T : 1))
 k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   extern __shared__ double sm[];
   __shared__ double red[32];
+  __shared__ double bcv[4];
   constexpr int NV = 4 * T;
   const int np = nd.np, ne = nd.Nx, S = nd.S;
   const int tid = threadIdx.x;
@@ -523,10 +545,67 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   c.dth = nd.dt * nd.theta; c.dte = nd.dt * (1.0 - nd.theta);
   c.c1_0 = v.f0 * sqrt(v.A00); c.c1_L = v.fL * sqrt(v.A0L);
   c.root = (a == nd.root_artery); c.leaf = nd.art_leaf[a] >= 0;
-  // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
-  c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
-  c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
-  if (c.root && inlet_index >= 0) c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
+  if (FUSED) {
+    // set_bcs for THIS artery inside its own CTA (an:767-786): warp 0 solves the
+    // junction at the inlet (the artery is a daughter there), warp 1 the junction
+    // at the outlet (the artery is its parent) or the Windkessel of a leaf.  A
+    // junction is therefore solved by the three CTAs of its vessels from the same
+    // inputs (bitwise identical results); its parent's CTA owns the bookkeeping
+    // (x -> jx_next, dex, counters).  All of it reads only Un of the `cur` buffers.
+    const int w = tid >> 5, lane = tid & 31;
+    if (w == 0) {
+      if (c.root) {
+        if (lane == 0) {
+          bcv[0] = nd.bc[ba * 4 + 0];
+          bcv[1] = inlet_index >= 0 ? nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index]
+                                    : nd.bc[ba * 4 + 1];
+        }
+      } else {
+        const int j = nd.art_jin[a];
+        double x[18], dex;
+        int solves;
+        uint32_t jfl;
+        junction_solve_warp(nd, cur, b, j, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
+        if (lane == 0) {
+          const bool first_daughter = nd.art_role[a] == 1;
+          bcv[0] = first_daughter ? x[12] : x[15];
+          bcv[1] = first_daughter ? x[3] : x[6];
+        }
+      }
+    } else if (w == 1) {
+      if (c.leaf) {
+        WkResult r = leaf_solve_warp(nd, cur, b, nd.art_leaf[a], log_slot);   // writes bc/dex/counters itself
+        if (lane == 0) { bcv[2] = r.A_out; bcv[3] = nd.bc[ba * 4 + 3]; }
+      } else {
+        const int j = nd.art_jout[a];
+        double x[18], dex;
+        int solves;
+        uint32_t jfl;
+        junction_solve_warp(nd, cur, b, j, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
+        if (lane == 0) {
+          bcv[2] = x[9]; bcv[3] = x[0];
+          double* xo = nd.jx_next + ((size_t)b * nd.nj + j) * 18;
+          for (int i = 0; i < 18; ++i) xo[i] = x[i];
+          nd.dex[ba] = dex;
+          nd.j_solves[b * nd.nj + j] = solves;
+          if (log_slot >= 0) nd.log_j[(size_t)log_slot * nd.nb * nd.nj + b * nd.nj + j] = solves;
+          atomicAdd(&nd.totals[1], (unsigned long long)solves);
+          if (jfl) atomicOr(&nd.flags[b], jfl);
+        }
+      }
+    }
+    __syncthreads();
+    c.gAin = bcv[0]; c.gqin = bcv[1]; c.gAout = bcv[2]; c.gqout = bcv[3];
+    if (tid == 0) {
+      nd.bc[ba * 4 + 0] = bcv[0]; nd.bc[ba * 4 + 1] = bcv[1];
+      nd.bc[ba * 4 + 2] = bcv[2]; nd.bc[ba * 4 + 3] = bcv[3];
+    }
+  } else {
+    // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
+    c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
+    c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
+    if (c.root && inlet_index >= 0) c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
+  }
   CellCoef ccu;
 #pragma unroll
   for (int g = 0; g < 3; ++g) { ccu.c1[g] = c.c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
@@ -816,6 +895,7 @@ struct af_net {
   int artery_threads = 256;
   size_t artery_smem = 0;
   int boundary_lanes = 32;
+  bool fused = false;              // af_net_step: set_bcs inside the artery CTAs (single networks)
   int boundary_block = 64;         // threads per CTA of k_boundary (AF_BOUNDARY_BLOCK overrides)
   std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
   int n_pending = 0;
@@ -856,24 +936,33 @@ extern "C" void af_desc_defaults(af_desc* d) {
 }
 
 template <int T>
-static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot) {
-  k_artery<T><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
+static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot, bool fused) {
+  if (fused && T >= 64)
+    k_artery<T, (T >= 64)><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
+  else
+    k_artery<T, false><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
   return cudaGetLastError();
 }
 
 template <int T>
 static cudaError_t prepare_artery(af_net* n) {
-  return cudaFuncSetAttribute(k_artery<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n->artery_smem);
+  cudaError_t e = cudaFuncSetAttribute(k_artery<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)n->artery_smem);
+  if (e == cudaSuccess && T >= 64)
+    e = cudaFuncSetAttribute(k_artery<T, (T >= 64)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)n->artery_smem);
+  return e;
 }
 
-static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot) {
+static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot,
+                              bool fused = false) {
   switch (n->artery_threads) {
-    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot);
-    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot);
-    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot);
-    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot);
-    case 512: return launch_artery<512>(n, ba0, count, inlet_index, log_slot);
-    default: return launch_artery<1024>(n, ba0, count, inlet_index, log_slot);
+    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot, fused);
+    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot, fused);
+    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot, fused);
+    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot, fused);
+    case 512: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused);
+    default: return launch_artery<1024>(n, ba0, count, inlet_index, log_slot, fused);
   }
 }
 
@@ -940,13 +1029,23 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
     for (int v = 0; v < 3; ++v)
       if (ia[v] < 0 || ia[v] >= nd.na) { af_net_destroy(n); return fail(AF_EINVAL, "junction index out of range"); }
   }
-  int *dp, *dd1, *dd2, *dla, *dal;
+  std::vector<int> art_jin(nd.na, -1), art_role(nd.na, 0), art_jout(nd.na, -1);
+  for (int j = 0; j < nd.nj; ++j) {
+    art_jout[d->junction_parent[j]] = j;
+    art_jin[d->junction_d1[j]] = j; art_role[d->junction_d1[j]] = 1;
+    art_jin[d->junction_d2[j]] = j; art_role[d->junction_d2[j]] = 2;
+  }
+  int *dp, *dd1, *dd2, *dla, *dal, *djin, *drole, *djout;
   AF_TRY(n->upload(&dp, d->junction_parent, nd.nj));
   AF_TRY(n->upload(&dd1, d->junction_d1, nd.nj));
   AF_TRY(n->upload(&dd2, d->junction_d2, nd.nj));
   AF_TRY(n->upload(&dla, d->leaf_artery, nd.nl));
   AF_TRY(n->upload(&dal, art_leaf.data(), nd.na));
+  AF_TRY(n->upload(&djin, art_jin.data(), nd.na));
+  AF_TRY(n->upload(&drole, art_role.data(), nd.na));
+  AF_TRY(n->upload(&djout, art_jout.data(), nd.na));
   nd.j_p = dp; nd.j_d1 = dd1; nd.j_d2 = dd2; nd.leaf_art = dla; nd.art_leaf = dal;
+  nd.art_jin = djin; nd.art_role = drole; nd.art_jout = djout;
   // parameters
   double *k1, *k2, *k3, *rho, *Re, *db, *p0, *Ru, *Rd, *L, *q0, *qins;
   AF_TRY(n->upload(&k1, d->k1, nd.nb)); AF_TRY(n->upload(&k2, d->k2, nd.nb)); AF_TRY(n->upload(&k3, d->k3, nd.nb));
@@ -981,6 +1080,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   AF_TRY(n->dalloc(&nd.bc, nba * 4));
   AF_TRY(n->dalloc(&nd.dex, nba));
   AF_TRY(n->dalloc(&nd.jx, (size_t)nd.nb * nd.nj * 18));
+  AF_TRY(n->dalloc(&nd.jx_next, (size_t)nd.nb * nd.nj * 18));
   AF_TRY(n->dalloc(&nd.art_its, nba));
   AF_TRY(n->dalloc(&nd.j_solves, (size_t)nd.nb * nd.nj));
   AF_TRY(n->dalloc(&nd.picard_its, (size_t)nd.nb * nd.nl));
@@ -1001,6 +1101,15 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   n->artery_smem = (size_t)AF_ARTERY_SMEM_PER_THREAD * n->artery_threads * sizeof(double);
   n->boundary_lanes = ((long long)nd.nb * (nd.nj + nd.nl) >= 148LL * 64) ? 1 : 32;
   n->boundary_block = 64;
+  // fused step (one launch per time step) needs two warps per artery for the two ends and is meant for
+  // single networks; every non-root artery must hang on a junction and every non-leaf must own one
+  n->fused = n->boundary_lanes == 32 && n->artery_threads >= 64 && nd.root_artery == 0;
+  // measured on the order-8 tree: 66.9 us/step fused vs 59.3 us two kernels (the boundary code spills under
+  // the artery kernel's 128-register cap), so the fused step is opt-in (AF_FUSE=1)
+  { const char* env = getenv("AF_FUSE"); if (!(env && atoi(env))) n->fused = false; }
+  for (int a = 0; a < nd.na && n->fused; ++a)
+    if ((a != 0 && art_jin[a] < 0) || (art_leaf[a] < 0 && art_jout[a] < 0)) n->fused = false;
+  if (const char* env = getenv("AF_NO_FUSE")) if (atoi(env)) n->fused = false;
   if (const char* env = getenv("AF_BOUNDARY_BLOCK")) n->boundary_block = atoi(env);
   cudaError_t e;
   switch (n->artery_threads) {
@@ -1083,8 +1192,13 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     }
     int log_slot = (n->log_n < n->log_cap) ? n->log_n++ : -1;
     int inlet = (step + 1) % Nt;                       // an:916
-    AF_CUDA(run_boundary(n, log_slot));
-    AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot));
+    if (n->fused) {
+      AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot, true));
+      std::swap(n->nd.jx, n->nd.jx_next);
+    } else {
+      AF_CUDA(run_boundary(n, log_slot));
+      AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot));
+    }
     n->cur ^= 1;
   }
   return AF_OK;

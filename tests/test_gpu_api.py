@@ -316,3 +316,32 @@ def test_nan_is_flagged_not_hidden():
     assert int(an._dev.get_flags()[0]) & 9 == 9
     with pytest.raises(RuntimeError):
         an.arteries[1].solve()
+
+
+def test_fused_step_equals_two_kernel_step(monkeypatch):
+    """AF_FUSE=1 makes af_net_step run set_bcs inside the artery CTAs (one launch
+    per step, every junction solved redundantly by the CTAs of its three
+    vessels); the default two-kernel path must give bitwise the same states,
+    junction unknowns, holders and counters."""
+    import bloodflow_b200.arteryfe as af
+    from bloodflow_b200.synthetic import tree_param
+
+    def run(no_fuse):
+        monkeypatch.setenv('AF_FUSE', '0' if no_fuse else '1')
+        an = af.ArteryNetwork(tree_param(4, Nx=300, Nt=4000))
+        an.define_x()
+        an._dev.set_counter_log(30)
+        an._dev.step(0, 30)
+        return (an._dev.get_state(), an._dev.get_junction_x(), an._dev.get_bc(), an._dev.get_dex(),
+                an._dev.fetch_counter_log(), an._dev.get_totals())
+
+    fused, plain = run(False), run(True)
+    for a, b in zip(fused[0], plain[0]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(fused[1], plain[1])
+    np.testing.assert_array_equal(fused[2][0, 1:], plain[2][0, 1:])       # the root's q_in holder is only
+    np.testing.assert_array_equal(fused[2][0, 0, 2:], plain[2][0, 0, 2:])  # written by the fused path
+    np.testing.assert_array_equal(fused[3], plain[3])
+    for a, b in zip(fused[4], plain[4]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(fused[5], plain[5])
