@@ -7,8 +7,6 @@ CUDA library.  An Artery built on its own (as the reference's unit tests do)
 owns a private one-vessel device network; inside an ArteryNetwork it is
 attached to the network's handle.
 """
-import copy
-
 import numpy as np
 
 from .. import _ffi
@@ -63,7 +61,9 @@ class Artery(object):
     def __init__(self, i, T, param, root=False, leaf=False):
         self.i, self.T = i, T
         self.root, self.leaf = root, leaf
-        self.param = copy.deepcopy(param)
+        # the reference deep-copies (ar:61); entries are only ever replaced, never mutated in place, so a
+        # per-artery dict over shared arrays is equivalent and keeps construction of large trees cheap
+        self.param = dict(param)
         for key in ('Ru', 'Rd', 'L'):
             self.param[key] = param[key][i]
         self._dev = None      # DeviceNetwork

@@ -375,15 +375,18 @@ class ArteryNetwork(object):
         if self.sol['store_pressure']:
             fields |= _ffi.AF_STORE_PRESSURE
         first_cycle = N_cycles - N_cycles_store
-        self._dev.set_store(mask, first_cycle, max(1, int(mask.sum()) * N_cycles_store), fields)
         total = N_cycles * Nt if n_steps is None else min(int(n_steps), N_cycles * Nt)
+        # snapshots that fall into the executed range (the store is sized for exactly those)
+        g = np.arange(total)
+        n_snap = int(np.count_nonzero((g // Nt >= first_cycle) & (mask[g % Nt] != 0)))
+        self._dev.set_store(mask, first_cycle, max(1, n_snap), fields)
         self._dev.step(0, total)
+        snaps = self._dev.fetch_snapshots()      # streams the snapshots out while the loop is still running
         self._dev.sync()
         flags = int(self._dev.get_flags()[0])
         if flags & _ffi.AF_FLAG_ARTERY_NOCONV:
             raise RuntimeError("Newton solver did not converge in an artery solve "
                                "(flags=0x%x; DOLFIN raises here, artery.py:244)" % flags)
-        snaps = self._dev.fetch_snapshots()
         # t is accumulated by repeated "t += dt" (artery_network.py:946)
         t_all = np.concatenate([[0.0], np.cumsum(np.full(N_cycles * Nt, self.dt))])
         res = {'t': t_all[snaps['step']], 'step': snaps['step']}

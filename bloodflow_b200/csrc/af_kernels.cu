@@ -888,6 +888,8 @@ struct af_net {
   int first_cycle = 0, max_snap = 0, fields = 0, n_snap = 0, snap_cap = 0;
   double *s_flow = nullptr, *s_area = nullptr, *s_press = nullptr, *s_outlet = nullptr;
   std::vector<int64_t> snap_step;
+  std::vector<cudaEvent_t> snap_event;   // recorded after the dump kernels of each snapshot
+  cudaStream_t copy_stream = nullptr;    // snapshots are copied out while the time loop keeps running
   // log
   int log_cap = 0, log_n = 0;
   // scratch for the fine-grained calls
@@ -1138,6 +1140,8 @@ extern "C" void af_net_destroy(af_net* n) {
   cudaSetDevice(n->device);
   if (n->stream) cudaStreamSynchronize(n->stream);
   for (void* p : n->allocs) cudaFree(p);
+  for (cudaEvent_t ev : n->snap_event) cudaEventDestroy(ev);
+  if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
   if (n->own_stream && n->stream) cudaStreamDestroy(n->stream);
   delete n;
 }
@@ -1172,6 +1176,12 @@ static int take_snapshot(af_net* n, int64_t g) {
     k_dump_outlet<<<(unsigned)((pl + 127) / 128), 128, 0, n->stream>>>(nd, n->cur, n->s_outlet + pl * n->n_snap);
     AF_CUDA(cudaGetLastError());
   }
+  if ((int)n->snap_event.size() <= n->n_snap) {
+    cudaEvent_t ev;
+    AF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    n->snap_event.push_back(ev);
+  }
+  AF_CUDA(cudaEventRecord(n->snap_event[n->n_snap], n->stream));
   n->snap_step.push_back(g);
   n->n_snap++;
   return AF_OK;
@@ -1286,16 +1296,23 @@ extern "C" int af_net_fetch_snapshots(af_net* n, double* flow, double* area, dou
   int rc = check(n);
   if (rc) return rc;
   const NetDev& nd = n->nd;
-  size_t per = (size_t)nd.nb * nd.na * nd.np * n->n_snap * sizeof(double);
-  if (flow) { if (!n->s_flow) return fail(AF_ESTATE, "flow not stored"); AF_CUDA(cudaMemcpyAsync(flow, n->s_flow, per, cudaMemcpyDeviceToHost, n->stream)); }
-  if (area) { if (!n->s_area) return fail(AF_ESTATE, "area not stored"); AF_CUDA(cudaMemcpyAsync(area, n->s_area, per, cudaMemcpyDeviceToHost, n->stream)); }
-  if (pressure) { if (!n->s_press) return fail(AF_ESTATE, "pressure not stored"); AF_CUDA(cudaMemcpyAsync(pressure, n->s_press, per, cudaMemcpyDeviceToHost, n->stream)); }
-  if (outlet_pressure) {
-    if (!n->s_outlet) return fail(AF_ESTATE, "outlet pressure not stored");
-    AF_CUDA(cudaMemcpyAsync(outlet_pressure, n->s_outlet, (size_t)nd.nb * nd.nl * n->n_snap * sizeof(double),
-                            cudaMemcpyDeviceToHost, n->stream));
+  if (flow && !n->s_flow) return fail(AF_ESTATE, "flow not stored");
+  if (area && !n->s_area) return fail(AF_ESTATE, "area not stored");
+  if (pressure && !n->s_press) return fail(AF_ESTATE, "pressure not stored");
+  if (outlet_pressure && !n->s_outlet) return fail(AF_ESTATE, "outlet pressure not stored");
+  if (!n->copy_stream) AF_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+  // Snapshot by snapshot on a second stream, each copy gated by the event recorded
+  // after its dump kernels: the downloads overlap the rest of the enqueued time loop.
+  const size_t per = (size_t)nd.nb * nd.na * nd.np, pl = (size_t)nd.nb * nd.nl;
+  for (int i = 0; i < n->n_snap; ++i) {
+    AF_CUDA(cudaStreamWaitEvent(n->copy_stream, n->snap_event[i], 0));
+    if (flow) AF_CUDA(cudaMemcpyAsync(flow + per * i, n->s_flow + per * i, per * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream));
+    if (area) AF_CUDA(cudaMemcpyAsync(area + per * i, n->s_area + per * i, per * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream));
+    if (pressure) AF_CUDA(cudaMemcpyAsync(pressure + per * i, n->s_press + per * i, per * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream));
+    if (outlet_pressure)
+      AF_CUDA(cudaMemcpyAsync(outlet_pressure + pl * i, n->s_outlet + pl * i, pl * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream));
   }
-  AF_CUDA(cudaStreamSynchronize(n->stream));
+  AF_CUDA(cudaStreamSynchronize(n->copy_stream));
   if (step) for (int i = 0; i < n->n_snap; ++i) step[i] = n->snap_step[i];
   return AF_OK;
 }

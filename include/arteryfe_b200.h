@@ -145,7 +145,9 @@ int af_net_snapshot_count(af_net* net, int32_t* count);
 /* Copy stored fields out; each of flow/area/pressure is
  * [count][n_networks][n_arteries][Nx+1] (NULL to skip), outlet_pressure is
  * [count][n_networks][n_leaves], step is [count] (global step index).
- * Synchronises the stream. */
+ * Returns when the snapshots taken so far have arrived; each download is gated
+ * on its own snapshot only, so calling this right after af_net_step overlaps
+ * the copies with the rest of the enqueued time loop. */
 int af_net_fetch_snapshots(af_net* net, double* flow, double* area, double* pressure, double* outlet_pressure,
                            int64_t* step);
 /* Device pointer of the outlet-pressure store [max_snapshots][n_networks][n_leaves]
