@@ -357,11 +357,14 @@ __device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b,
   leaf_solve_warp(nd, cur, b, l, log_slot);
 }
 
-__global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
+// WARP = true: one warp per task (single networks); false: one thread per task
+// (ensembles).  Two instantiations keep each kernel's code -- and the instruction
+// cache footprint of the lone warp that runs a task -- small.
+template <bool WARP>
+__global__ void k_boundary(NetDev nd, int cur, int log_slot) {
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
-  if (lanes == 32) {
-    // one warp per task
+  if (WARP) {
     long long task = gt >> 5;
     if (task < n_j) {
       junction_task_warp(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
@@ -369,14 +372,14 @@ __global__ void k_boundary(NetDev nd, int cur, int lanes, int log_slot) {
       task -= n_j;
       leaf_task_warp(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
     }
-    return;
-  }
-  long long task = gt;
-  if (task < n_j) {
-    junction_task(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
-  } else if (task < n_j + n_l) {
-    task -= n_j;
-    leaf_task(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+  } else {
+    long long task = gt;
+    if (task < n_j) {
+      junction_task(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
+    } else if (task < n_j + n_l) {
+      task -= n_j;
+      leaf_task(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+    }
   }
 }
 
@@ -974,7 +977,10 @@ static cudaError_t run_boundary(const af_net* n, int log_slot) {
   int block = n->boundary_block;
   long long grid = (threads + block - 1) / block;
   if (grid == 0) return cudaSuccess;
-  k_boundary<<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, n->boundary_lanes, log_slot);
+  if (n->boundary_lanes == 32)
+    k_boundary<true><<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, log_slot);
+  else
+    k_boundary<false><<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, log_slot);
   return cudaGetLastError();
 }
 
