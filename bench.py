@@ -99,6 +99,17 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    try:
+        with open(path) as fh:
+            t = json.load(fh)[kernel]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -293,7 +304,9 @@ def main():
             "cycles_per_sec_per_network": 1.0 / (ms_total * 1e-3 / K * args.Nt),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / peaks["hbm_gbs"],
+                "traffic": measured_traffic("k_artery<256>") if (args.order, args.Nx) == (ORDER, NX) else None,
+                "peak_kind": peak_kind,
                 "kernel": "k_artery", "kernel_us": art_us, "kernel_share_of_step": phase['artery_share'],
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "note": "32 B per vertex-step (read A,q; write A,q), untapered tree streams no coefficients; "

@@ -343,7 +343,8 @@ class ArteryNetwork(object):
         for key, value in (
                 ('order', self.nondim['order']), ('Nx', self.geo['Nx']),
                 ('Nt', self.sol['Nt_store'] * N_cycles_store), ('T0', self.T * (N_cycles - N_cycles_store)),
-                ('T', self.T * N_cycles), ('L', str(self.nondim['L'])[1:-1]), ('rc', self.nondim['rc']),
+                ('T', self.T * N_cycles), ('L', ' '.join(repr(float(v)) for v in self.nondim['L'])),
+                ('rc', self.nondim['rc']),
                 ('qc', self.nondim['qc']), ('rho', self.nondim['rho']),
                 ('mesh_locations', ','.join(mesh_locations)), ('names', ','.join(names)),
                 ('locations', ','.join(locations))):

@@ -398,6 +398,9 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
 // CTAs per SM, so all 255 arteries are co-resident.
 // ---------------------------------------------------------------------------
 #define AF_ARTERY_SMEM_PER_THREAD 48
+#ifndef AF_T32_BLOCKS
+#define AF_T32_BLOCKS 16     // resident one-warp CTAs per SM the T = 32 kernel is compiled for
+#endif
 
 template <int T>
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -514,7 +517,7 @@ __device__ __forceinline__ double assemble_pass(const ArteryCtx& c, const CellCo
 }
 
 template <int T, bool FUSED>
-__global__ void __launch_bounds__(T, (T <= 256 ? 512 / T : 1))
+__global__ void __launch_bounds__(T, (T == 32 ? AF_T32_BLOCKS : (T <= 256 ? 512 / T : 1)))
 k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   extern __shared__ double sm[];
   __shared__ double red[32];
@@ -621,29 +624,21 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   int it = 0;
   double r_first = 0.0;
   uint32_t fl = 0;
-  bool redo = false;
   for (;;) {
     const bool first = (it == 0);
-    // The Jacobian is assembled together with the residual while a further
-    // Newton step is likely (it < 2: 1.7 steps on average); later passes are
-    // usually the converged one, so they assemble the residual only and are
-    // repeated with the Jacobian in the rare case the test fails.
-    const bool jac = (it < 2) || redo;
     // ---- cells, rows, level 0 of the reduction (own part) -----------------------
-    double part;
+    // The Jacobian is always assembled with the residual: a residual-only variant
+    // for the (usually converged) last pass was measured slower -- the second copy
+    // of the assembly code costs more instruction-cache misses than the skipped
+    // derivative terms save (tree 59.3 -> 57.7 us/step, ensemble +8 % without it).
     Row rb, rd;
-    if (jac)
-      part = assemble_pass<T, true>(c, ccu, tab, S, sA, sq, pb, pa, pc, first, EA, Eq, rb, rd);
-    else
-      part = assemble_pass<T, false>(c, ccu, tab, S, sA, sq, pb, pa, pc, first, EA, Eq, rb, rd);
+    double part = assemble_pass<T, true>(c, ccu, tab, S, sA, sq, pb, pa, pc, first, EA, Eq, rb, rd);
     double r = sqrt(block_sum<T>(part, red));     // its two barriers also publish pa/pc
     // ---- [3P] NewtonSolver::converged ---------------------------------------
     if (first) r_first = r;
     if (r / r_first < nd.newton_rtol || r < nd.newton_atol) break;
     if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
     if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
-    if (!jac) { redo = true; continue; }      // same iterate again, now with the Jacobian
-    redo = false;
     // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------
     if (tid + 1 < T) {
       Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
