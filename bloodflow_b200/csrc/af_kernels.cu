@@ -362,6 +362,11 @@ __device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b,
 // cache footprint of the lone warp that runs a task -- small.
 template <bool WARP>
 __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
+  // Programmatic dependent launch: the artery kernel of the same step may become
+  // resident now and run its prologue (vessel constants, Un -> shared memory)
+  // under this kernel; it waits in cudaGridDependencySynchronize() before it
+  // reads the Dirichlet data written here.
+  cudaTriggerProgrammaticLaunchCompletion();
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
   if (WARP) {
@@ -607,6 +612,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       nd.bc[ba * 4 + 2] = bcv[2]; nd.bc[ba * 4 + 3] = bcv[3];
     }
   } else {
+    // everything above only needs the previous artery kernel's output; the
+    // Dirichlet data comes from the boundary kernel of this step
+    cudaGridDependencySynchronize();
     // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
     c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
     c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
@@ -895,6 +903,7 @@ struct af_net {
   int artery_threads = 256;
   size_t artery_smem = 0;
   int boundary_lanes = 32;
+  bool pdl = true;                 // programmatic dependent launch of k_artery (AF_NO_PDL=1 disables)
   bool fused = false;              // af_net_step: set_bcs inside the artery CTAs (single networks)
   int boundary_block = 64;         // threads per CTA of k_boundary (AF_BOUNDARY_BLOCK overrides)
   std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
@@ -937,11 +946,23 @@ extern "C" void af_desc_defaults(af_desc* d) {
 
 template <int T>
 static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot, bool fused) {
-  if (fused && T >= 64)
+  if (fused && T >= 64) {
     k_artery<T, (T >= 64)><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
-  else
-    k_artery<T, false><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
-  return cudaGetLastError();
+    return cudaGetLastError();
+  }
+  // programmatic stream serialisation: may start while the preceding kernel of the
+  // stream (k_boundary, which triggers early) is still running; see k_artery
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)count);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = n->artery_smem;
+  cfg.stream = n->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = n->pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_artery<T, false>, n->nd, n->cur, ba0, inlet_index, log_slot);
 }
 
 template <int T>
@@ -1113,6 +1134,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   for (int a = 0; a < nd.na && n->fused; ++a)
     if ((a != 0 && art_jin[a] < 0) || (art_leaf[a] < 0 && art_jout[a] < 0)) n->fused = false;
   if (const char* env = getenv("AF_NO_FUSE")) if (atoi(env)) n->fused = false;
+  if (const char* env = getenv("AF_NO_PDL")) if (atoi(env)) n->pdl = false;
   if (const char* env = getenv("AF_BOUNDARY_BLOCK")) n->boundary_block = atoi(env);
   cudaError_t e;
   switch (n->artery_threads) {
