@@ -458,65 +458,81 @@ __device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const CellCoe
   return ci;
 }
 
-// One assembly pass of a thread: its four cells and four vertex rows, streamed so
-// that at most two rows are live: a and c are turned into their eliminated form
-// (x = g - P x_l - Q x_r, parked in shared memory) as soon as they are complete
-// and applied to b and d (level 0 of the cyclic reduction, own part).  This is
-// done before the convergence test is known; on the converged pass it is
-// discarded.  The right part of the last cell travels to the next thread through
-// `xch` (one CTA barrier).  Returns the thread's share of ||R||^2.
-template <int T, bool JAC>
-__device__ __forceinline__ double assemble_pass(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
-                                                const double* sA, const double* sq, double* xch, double* pa,
-                                                double* pc, bool first, double* EA, double* Eq, Row& rb, Row& rd) {
+// An assembly pass of a thread has two halves separated by one CTA barrier.
+// (1) cells_to_smem: the flux/source/Jacobian integrals of its four cells, which
+// depend on the iterate U only (not on the Dirichlet data), go to shared memory:
+// cell k of thread t into slot t of region k (pa, pb, pc, lo; 10 doubles each).
+template <int T>
+__device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
+                                              const double* sA, const double* sq, double* pa, double* pb,
+                                              double* pc, double* lo) {
   const int tid = threadIdx.x, i0 = 4 * tid;
-  // the last cell first: its right part belongs to the next thread's vertex a
-  CellInt c3 = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0 + 3);
-  xch[0 * T + tid] = c3.Gr;
-  if (JAC) {
-    xch[1 * T + tid] = c3.JA[2]; xch[2 * T + tid] = c3.JA[3];
-    xch[3 * T + tid] = c3.Jq[2]; xch[4 * T + tid] = c3.Jq[3];
+  double* reg[4] = {pa, pb, pc, lo};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    CellInt ci = artery_cell<true>(c, ccu, tab, S, sA, sq, i0 + k);
+    double* r = reg[k];
+    r[0 * T + tid] = ci.Gl; r[1 * T + tid] = ci.Gr;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { r[(2 + m) * T + tid] = ci.JA[m]; r[(6 + m) * T + tid] = ci.Jq[m]; }
   }
-  __syncthreads();
-  CellInt prev;
-  cell_zero(prev);
-  if (tid > 0) {
-    prev.Gr = xch[0 * T + tid - 1];
-    if (JAC) {
-      prev.JA[2] = xch[1 * T + tid - 1]; prev.JA[3] = xch[2 * T + tid - 1];
-      prev.Jq[2] = xch[3 * T + tid - 1]; prev.Jq[3] = xch[4 * T + tid - 1];
-    }
-  }
+}
+
+__device__ __forceinline__ void load_cell_left_part(const double* r, int T, int t, CellInt& ci) {
+  ci.Gl = r[0 * T + t];
+  ci.JA[0] = r[2 * T + t]; ci.JA[1] = r[3 * T + t];
+  ci.Jq[0] = r[6 * T + t]; ci.Jq[1] = r[7 * T + t];
+}
+
+__device__ __forceinline__ void load_cell_right_part(const double* r, int T, int t, CellInt& ci) {
+  ci.Gr = r[1 * T + t];
+  ci.JA[2] = r[4 * T + t]; ci.JA[3] = r[5 * T + t];
+  ci.Jq[2] = r[8 * T + t]; ci.Jq[3] = r[9 * T + t];
+}
+
+// (2) rows_from_smem: the four vertex rows, streamed so that at most two rows are
+// live: a and c are turned into their eliminated form (x = g - P x_l - Q x_r,
+// parked in shared memory, over the slot of the cell just consumed) as soon as
+// they are complete and applied to b and d (level 0 of the cyclic reduction, own
+// part).  This is done before the convergence test is known; on the converged
+// pass it is discarded.  Returns the thread's share of ||R||^2.
+template <int T>
+__device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const double* sA, const double* sq, double* pa,
+                                                 double* pb, double* pc, const double* lo, bool first, double* EA,
+                                                 double* Eq, Row& rb, Row& rd) {
+  const int tid = threadIdx.x, i0 = 4 * tid;
+  CellInt left, own;
+  cell_zero(left);
+  cell_zero(own);
+  if (tid > 0) load_cell_right_part(lo, T, tid - 1, left);     // last cell of the previous thread
+  load_cell_left_part(pa, T, tid, own);
   double part = 0.0;
-  CellInt ck = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0);
   {
     Row ra;
-    build_row<JAC>(c, i0, first, sA, sq, prev, ck, EA[0], Eq[0], ra);
+    build_row<true>(c, i0, first, sA, sq, left, own, EA[0], Eq[0], ra);
     part += ra.r[0] * ra.r[0] + ra.r[1] * ra.r[1];
-    prev = ck;
-    ck = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0 + 1);
-    build_row<JAC>(c, i0 + 1, first, sA, sq, prev, ck, EA[1], Eq[1], rb);
+    load_cell_right_part(pa, T, tid, left);
+    load_cell_left_part(pb, T, tid, own);
+    build_row<true>(c, i0 + 1, first, sA, sq, left, own, EA[1], Eq[1], rb);
     part += rb.r[0] * rb.r[0] + rb.r[1] * rb.r[1];
-    if (JAC) {
-      Elim ea = make_elim(ra);
-      park(pa, T, tid, ea);
-      apply_left(rb, ea);
-    }
+    Elim ea = make_elim(ra);
+    park(pa, T, tid, ea);
+    apply_left(rb, ea);
   }
-  prev = ck;
-  ck = artery_cell<JAC>(c, ccu, tab, S, sA, sq, i0 + 2);
   {
     Row rc;
-    build_row<JAC>(c, i0 + 2, first, sA, sq, prev, ck, EA[2], Eq[2], rc);
+    load_cell_right_part(pb, T, tid, left);
+    load_cell_left_part(pc, T, tid, own);
+    build_row<true>(c, i0 + 2, first, sA, sq, left, own, EA[2], Eq[2], rc);
     part += rc.r[0] * rc.r[0] + rc.r[1] * rc.r[1];
-    build_row<JAC>(c, i0 + 3, first, sA, sq, ck, c3, EA[3], Eq[3], rd);
+    load_cell_right_part(pc, T, tid, left);
+    load_cell_left_part(lo, T, tid, own);
+    build_row<true>(c, i0 + 3, first, sA, sq, left, own, EA[3], Eq[3], rd);
     part += rd.r[0] * rd.r[0] + rd.r[1] * rd.r[1];
-    if (JAC) {
-      Elim ec = make_elim(rc);
-      park(pc, T, tid, ec);
-      apply_right(rb, ec);
-      apply_left(rd, ec);
-    }
+    Elim ec = make_elim(rc);
+    park(pc, T, tid, ec);
+    apply_right(rb, ec);
+    apply_left(rd, ec);
   }
   return part;
 }
@@ -611,14 +627,6 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       nd.bc[ba * 4 + 0] = bcv[0]; nd.bc[ba * 4 + 1] = bcv[1];
       nd.bc[ba * 4 + 2] = bcv[2]; nd.bc[ba * 4 + 3] = bcv[3];
     }
-  } else {
-    // everything above only needs the previous artery kernel's output; the
-    // Dirichlet data comes from the boundary kernel of this step
-    cudaGridDependencySynchronize();
-    // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
-    c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
-    c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
-    if (c.root && inlet_index >= 0) c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
   }
   CellCoef ccu;
 #pragma unroll
@@ -634,13 +642,27 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   uint32_t fl = 0;
   for (;;) {
     const bool first = (it == 0);
-    // ---- cells, rows, level 0 of the reduction (own part) -----------------------
+    // ---- cells -> shared memory, then rows and level 0 of the reduction ------------
     // The Jacobian is always assembled with the residual: a residual-only variant
     // for the (usually converged) last pass was measured slower -- the second copy
     // of the assembly code costs more instruction-cache misses than the skipped
     // derivative terms save (tree 59.3 -> 57.7 us/step, ensemble +8 % without it).
     Row rb, rd;
-    double part = assemble_pass<T, true>(c, ccu, tab, S, sA, sq, pb, pa, pc, first, EA, Eq, rb, rd);
+    cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
+    if (!FUSED && first) {
+      // Everything up to here (vessel constants, U <- Un, the cell integrals of the
+      // first pass) only needs the previous artery kernel's output and has been
+      // running under the boundary kernel of this step (programmatic dependent
+      // launch); the Dirichlet data it writes is needed from here on.
+      cudaGridDependencySynchronize();
+      // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
+      c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
+      c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
+      if (c.root && inlet_index >= 0)
+        c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
+    }
+    __syncthreads();
+    double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
     double r = sqrt(block_sum<T>(part, red));     // its two barriers also publish pa/pc
     // ---- [3P] NewtonSolver::converged ---------------------------------------
     if (first) r_first = r;
