@@ -366,6 +366,10 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
   // resident now and run its prologue (vessel constants, Un -> shared memory)
   // under this kernel; it waits in cudaGridDependencySynchronize() before it
   // reads the Dirichlet data written here.
+  // This kernel itself may have been launched early (under the artery kernel of the
+  // previous step): wait for that kernel's Un before anything else, and only then
+  // let the next artery kernel in.
+  cudaGridDependencySynchronize();
   cudaTriggerProgrammaticLaunchCompletion();
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
@@ -553,6 +557,8 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   double* pb = pa + 10 * T;
   double* pc = pb + 10 * T;
 
+  // the next boundary kernel may be made resident early; it waits for this grid to finish
+  cudaTriggerProgrammaticLaunchCompletion();
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
   const Vessel v = nd.ves[ba];
@@ -1015,11 +1021,18 @@ static cudaError_t run_boundary(const af_net* n, int log_slot) {
   int block = n->boundary_block;
   long long grid = (threads + block - 1) / block;
   if (grid == 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(block);
+  cfg.stream = n->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = n->pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (n->boundary_lanes == 32)
-    k_boundary<true><<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, log_slot);
-  else
-    k_boundary<false><<<(unsigned)grid, block, 0, n->stream>>>(n->nd, n->cur, log_slot);
-  return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, k_boundary<true>, n->nd, n->cur, log_slot);
+  return cudaLaunchKernelEx(&cfg, k_boundary<false>, n->nd, n->cur, log_slot);
 }
 
 extern "C" int af_net_create(const af_desc* d, af_net** out) {
