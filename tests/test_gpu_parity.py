@@ -276,3 +276,42 @@ def test_ensemble_driver_matches_single_member_runs():
     np.testing.assert_allclose(stats['mean'].cpu().numpy(), op.mean(axis=1), rtol=1e-13)
     np.testing.assert_allclose(stats['max'].cpu().numpy(), op.max(axis=1), rtol=0)
     assert not (ens.flags() & 1).any()
+
+
+@pytest.mark.parametrize('order,Nx,Nt,steps', ((8, 1000, 8000, 60), (5, 500, 4000, 60)))
+def test_full_size_trees_short_horizon(order, Nx, Nt, steps):
+    """BASELINE configs C4 (255 x 1001 vertices) and C3 (31 x 501) at FULL size
+    against the C oracle.  On these fine-grid synthetic trees the reference
+    scheme itself amplifies perturbations (a 1e-13 change grows ~10x every 30
+    steps, tests/test_oracle_c.py::test_fine_grid_trees_are_sensitive and
+    DESIGN.md section 2), so element-wise 1e-9 agreement is only meaningful over a
+    short horizon; beyond it any two implementations decorrelate."""
+    import bloodflow_b200.arteryfe as af
+    from bloodflow_b200.synthetic import tree_param
+    from oracle import arteryfe_oracle as ao
+    from oracle.oracle_c import COracle
+    an = af.ArteryNetwork(tree_param(order, Nx=Nx, Nt=Nt))
+    an.define_x()
+    an._dev.set_counter_log(steps)
+    an._dev.step(0, steps)
+    A, q = an._dev.get_state()
+    p = tree_param(order, Nx=Nx, Nt=Nt)
+    c = COracle(ao.OracleNetwork(p.param, p.geo, p.solution))
+    failed, la, lj = c.step(0, steps, nthreads=0, log=True)
+    assert failed == 0
+    Ao, qo = c.state()
+    np.testing.assert_allclose(A[0], Ao, rtol=1e-9)
+    np.testing.assert_allclose(q[0], qo, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(an._dev.get_junction_x()[0], c.x(), rtol=1e-9)
+    art, jun, _ = an._dev.fetch_counter_log()
+    assert np.count_nonzero(art[:, 0] != la) == 0
+    # Junction Newton: the stopping test ||f|| < 1e-10 is applied to an f whose own
+    # round-off is ~1e-11 (pressure terms of size 1e4-1e5), so an iterate whose norm
+    # lands within ~10 % of the threshold can be counted 2 or 3 by two correct
+    # implementations (x then differs by ~1e-11).  Such near-ties do not occur on the
+    # golden cases (0 of ~4 000 solves) nor on C4 here (0 of 7 620), but do on C3
+    # (3 of 900 measured): the count must agree on at least 99 % of the solves.
+    mism = np.count_nonzero(jun[:, 0] != lj)
+    assert mism <= 0.01 * lj.size, (mism, lj.size)
+    assert np.abs(jun[:, 0] - lj).max() <= 1
+    assert int(an._dev.get_flags()[0]) & (1 | 8) == 0
