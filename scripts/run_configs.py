@@ -56,7 +56,8 @@ def run(name, param, **kw):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--configs', default='c1,c1head,c2,c3,c4')
+    ap.add_argument('--configs', default='c1,c1head,c2,c3,c4,c5')
+    ap.add_argument('--members', type=int, default=4096)
     args = ap.parse_args()
     want = args.configs.split(',')
     if 'c1' in want:
@@ -73,6 +74,29 @@ def main():
         run('C3 order-5 tree Nx=500 Nt=4000, 2 cycles', tree_param(5, Nx=500, Nt=4000, N_cycles=2, Nt_store=100))
     if 'c4' in want:
         run('C4 order-8 tree Nx=1000 Nt=8000, 4 cycles', tree_param(8, Nx=1000, Nt=8000, N_cycles=4, Nt_store=100))
+    if 'c5' in want:
+        from bloodflow_b200 import ensemble as en
+        base = tree_param(4, Nx=100, Nt=2000, N_cycles=2, Nt_store=100)
+        t0 = time.perf_counter()
+        ens = en.EnsembleNetwork(base, args.members)
+        op = ens.solve(n_cycles=2)
+        dt = time.perf_counter() - t0
+        flags = ens.flags()
+        nd = ens.nominal.nondim
+        p = unit_to_mmHg(redimensionalise(nd['rc'], nd['qc'], nd['rho'], op, 'pressure'))
+        tot = ens.dev.get_totals()
+        steps = 2 * 2000
+        print(json.dumps({
+            "config": "C5 UQ ensemble, %d perturbed order-4 networks (Nx=100, Nt=2000), 2 cycles" % args.members,
+            "members": args.members, "vertices": ens.vertices, "steps": steps, "seconds": dt,
+            "node_steps_per_s": ens.vertices * steps / dt, "cycles_per_s_all_networks": args.members * 2 / dt,
+            "members_with_artery_nonconvergence": int(np.count_nonzero(flags & 1)),
+            "members_with_nonfinite": int(np.count_nonzero(flags & 8)),
+            "artery_newton_its_per_solve": tot[0] / float(ens.n_networks * ens.dev.na * steps),
+            "junction_solves_per_step": tot[1] / float(ens.n_networks * ens.dev.nj * steps),
+            "outlet_p_mmHg_mean": float(p.mean()), "outlet_p_mmHg_std_over_members": float(p.std(axis=1).mean()),
+            "outlet_p_mmHg_min": float(p.min()), "outlet_p_mmHg_max": float(p.max()), "snapshots": int(op.shape[0]),
+        }), flush=True)
 
 
 if __name__ == '__main__':
