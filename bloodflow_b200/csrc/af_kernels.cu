@@ -215,17 +215,19 @@ __device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, 
 // one warp per junction (single networks): lane v < 3 owns vessel v; the 3x3
 // solves are done redundantly by every lane, so no result has to travel back.
 // On return every lane holds x; dex, solves, fl are warp-uniform.
-__device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, int b, int j, const double* xg,
-                                                    double* x, double& dex, int& solves, uint32_t& fl) {
+// `ia` (the three vessels of the junction) and `ves` (the constants of this lane's
+// vessel, ia[lane % 3]) are loaded by the caller: they do not depend on the state,
+// so the boundary kernel fetches them before its grid-dependency wait.
+__device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, int b, int j, const int* ia,
+                                                    const Vessel& ves, const double* xg, double* x, double& dex,
+                                                    int& solves, uint32_t& fl) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v = lane % 3;
-  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
   const int ba = b * nd.na + ia[v];
   const size_t off = (size_t)ba * nd.S;
   const double* A = nd.A[cur] + off;
   const double* q = nd.q[cur] + off;
-  const Vessel ves = nd.ves[ba];
   // adjust_bifurcation_step (an:713-737): min over the three vessels
   double M = junction_cfl(ves, v, A, q, nd.Nx);
   {
@@ -273,14 +275,14 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   }
 }
 
-__device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, int log_slot) {
+__device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, const int* ia,
+                                                   const Vessel& ves, int log_slot) {
   double x[18], dex;
   int solves;
   uint32_t fl;
   const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
-  junction_solve_warp(nd, cur, b, j, xg, x, dex, solves, fl);
+  junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl);
   if ((threadIdx.x & 31) != 0) return;
-  int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
   junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot);
 }
 
@@ -301,15 +303,14 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
 // one warp per leaf (single networks): lanes 0..2 take the three stencil points
 // L-2dex, L-dex, L of windkessel() (an:383-390), lanes 0..1 the two half steps
 // (an:393-398); the Picard loop is inherently serial.
-__device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, int b, int l, int log_slot) {
+__device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, int b, int l, int ba,
+                                                    const Vessel& ves, int log_slot) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = lane % 3;
-  const int ba = b * nd.na + nd.leaf_art[l];
   const size_t off = (size_t)ba * nd.S;
   const double* A = nd.A[cur] + off;
   const double* q = nd.q[cur] + off;
-  const Vessel ves = nd.ves[ba];
   const double L = ves.L, dt = nd.dt;
   // adjust_dex (ar:349-365)
   Coef cL;
@@ -353,35 +354,45 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   return r;
 }
 
-__device__ __forceinline__ void leaf_task_warp(const NetDev& nd, int cur, int b, int l, int log_slot) {
-  leaf_solve_warp(nd, cur, b, l, log_slot);
-}
+
 
 // WARP = true: one warp per task (single networks); false: one thread per task
 // (ensembles).  Two instantiations keep each kernel's code -- and the instruction
 // cache footprint of the lone warp that runs a task -- small.
 template <bool WARP>
 __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
-  // Programmatic dependent launch: the artery kernel of the same step may become
-  // resident now and run its prologue (vessel constants, Un -> shared memory)
-  // under this kernel; it waits in cudaGridDependencySynchronize() before it
-  // reads the Dirichlet data written here.
-  // This kernel itself may have been launched early (under the artery kernel of the
-  // previous step): wait for that kernel's Un before anything else, and only then
-  // let the next artery kernel in.
-  cudaGridDependencySynchronize();
-  cudaTriggerProgrammaticLaunchCompletion();
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
   if (WARP) {
+    // Topology and vessel constants do not depend on the state: fetch them first,
+    // they arrive while this kernel -- which may have been made resident under
+    // the artery kernel of the previous step (programmatic dependent launch) --
+    // waits for that kernel's Un.
     long long task = gt >> 5;
-    if (task < n_j) {
-      junction_task_warp(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
-    } else if (task < n_j + n_l) {
+    const int v = (threadIdx.x & 31) % 3;
+    int b = 0, j = 0, l = 0, ba = 0, ia[3] = {0, 0, 0};
+    const bool is_junction = task < n_j, is_leaf = !is_junction && task < n_j + n_l;
+    if (is_junction) {
+      b = (int)(task / nd.nj); j = (int)(task % nd.nj);
+      ia[0] = nd.j_p[j]; ia[1] = nd.j_d1[j]; ia[2] = nd.j_d2[j];
+      ba = b * nd.na + ia[v];
+    } else if (is_leaf) {
       task -= n_j;
-      leaf_task_warp(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+      b = (int)(task / nd.nl); l = (int)(task % nd.nl);
+      ba = b * nd.na + nd.leaf_art[l];
     }
+    const Vessel ves = nd.ves[ba];
+    cudaGridDependencySynchronize();
+    // only now may the artery kernel of THIS step start its prologue: it reads the
+    // Un that the previous artery kernel has just finished writing
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (is_junction)
+      junction_task_warp(nd, cur, b, j, ia, ves, log_slot);
+    else if (is_leaf)
+      leaf_solve_warp(nd, cur, b, l, ba, ves, log_slot);
   } else {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     long long task = gt;
     if (task < n_j) {
       junction_task(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
@@ -598,7 +609,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
         double x[18], dex;
         int solves;
         uint32_t jfl;
-        junction_solve_warp(nd, cur, b, j, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
+        const int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+        const Vessel jves = nd.ves[b * nd.na + ia[lane % 3]];
+        junction_solve_warp(nd, cur, b, j, ia, jves, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
         if (lane == 0) {
           const bool first_daughter = nd.art_role[a] == 1;
           bcv[0] = first_daughter ? x[12] : x[15];
@@ -607,14 +620,16 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       }
     } else if (w == 1) {
       if (c.leaf) {
-        WkResult r = leaf_solve_warp(nd, cur, b, nd.art_leaf[a], log_slot);   // writes bc/dex/counters itself
+        WkResult r = leaf_solve_warp(nd, cur, b, nd.art_leaf[a], ba, v, log_slot);   // writes bc/dex/counters itself
         if (lane == 0) { bcv[2] = r.A_out; bcv[3] = nd.bc[ba * 4 + 3]; }
       } else {
         const int j = nd.art_jout[a];
         double x[18], dex;
         int solves;
         uint32_t jfl;
-        junction_solve_warp(nd, cur, b, j, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
+        const int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+        const Vessel jves = nd.ves[b * nd.na + ia[lane % 3]];
+        junction_solve_warp(nd, cur, b, j, ia, jves, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
         if (lane == 0) {
           bcv[2] = x[9]; bcv[3] = x[0];
           double* xo = nd.jx_next + ((size_t)b * nd.nj + j) * 18;
