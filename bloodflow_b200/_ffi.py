@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libarteryfe_b200.so')
+# the in-tree build; ARTERYFE_B200_LIB points at a library installed elsewhere
+LIB_PATH = os.environ.get('ARTERYFE_B200_LIB') or os.path.join(_HERE, 'csrc', 'libarteryfe_b200.so')
 
 AF_ABI_VERSION = 1
 AF_OK, AF_EINVAL, AF_ENODEVICE, AF_ECUDA, AF_ENOMEM, AF_ESTATE = 0, -1, -2, -3, -4, -5

@@ -54,6 +54,17 @@ def test_no_cpu_fallback():
     assert e.value.code == -2
 
 
+def test_missing_library_fails_loudly(tmp_path):
+    """No built CUDA library => the package refuses to import its compute layer
+    (there is nothing to fall back to)."""
+    import sys
+    env = dict(os.environ, ARTERYFE_B200_LIB=str(tmp_path / 'nope.so'), PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, '-c', 'import bloodflow_b200.arteryfe'], env=env, capture_output=True,
+                         text=True)
+    assert out.returncode != 0
+    assert 'ImportError' in out.stderr and 'no CPU fallback' in out.stderr.replace('There is no CPU fallback', 'no CPU fallback')
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, 'bloodflow_b200')):
         for f in files:
