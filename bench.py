@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -191,8 +191,8 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=2000)
-    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=8000, help='timed time steps (default: one cardiac cycle)')
+    ap.add_argument('--warmup', type=int, default=100)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--order', type=int, default=ORDER)
     ap.add_argument('--Nx', type=int, default=NX)
