@@ -422,11 +422,25 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
 #define AF_T32_BLOCKS 16     // resident one-warp CTAs per SM the T = 32 kernel is compiled for
 #endif
 
+// CTA-wide barrier; a one-warp CTA (T = 32, the ensemble kernel) only needs the
+// warp-level one.
+template <int T>
+__device__ __forceinline__ void cta_sync() {
+  if (T == 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+
 template <int T>
 __device__ __forceinline__ double block_sum(double v, double* red) {
   // fixed-order: lanes by xor-tree, warps in index order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (T == 32) {
+    __syncwarp();          // orders the shared-memory writes of the pass, like the barriers below
+    return v;
+  }
   int w = threadIdx.x >> 5;
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[w] = v;
@@ -642,7 +656,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
         }
       }
     }
-    __syncthreads();
+    cta_sync<T>();
     c.gAin = bcv[0]; c.gqin = bcv[1]; c.gAout = bcv[2]; c.gqout = bcv[3];
     if (tid == 0) {
       nd.bc[ba * 4 + 0] = bcv[0]; nd.bc[ba * 4 + 1] = bcv[1];
@@ -656,7 +670,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   const double* tab = slot >= 0 ? nd.cellcoef + (size_t)slot * 9 * S : nullptr;
   const int i0 = 4 * tid;
   double EA[4], Eq[4];          // explicit part of the residual of the own vertices
-  __syncthreads();
+  cta_sync<T>();
 
   int it = 0;
   double r_first = 0.0;
@@ -682,7 +696,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       if (c.root && inlet_index >= 0)
         c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
     }
-    __syncthreads();
+    cta_sync<T>();
     double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
     double r = sqrt(block_sum<T>(part, red));     // its two barriers also publish pa/pc
     // ---- [3P] NewtonSolver::converged ---------------------------------------
@@ -700,7 +714,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       park(pb, T, tid, eb);
       apply_left(rd, eb);
     }
-    __syncthreads();
+    cta_sync<T>();
     if (tid + 1 < T) {
       Elim en = unpark(pb, T, tid + 1);      // vertex b of the next thread
       apply_right(rd, en);
@@ -718,17 +732,17 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
 #pragma unroll 1
       for (int sdist = 1; sdist < T; sdist *= 2) {
         park(buf, T, tid, make_elim(rd));
-        __syncthreads();
+        cta_sync<T>();
         if (tid >= sdist) apply_left(rd, unpark(buf, T, tid - sdist));
         if (tid + sdist < T) apply_right(rd, unpark(buf, T, tid + sdist));
-        __syncthreads();
+        cta_sync<T>();
       }
       double inv[4];
       inv2v(rd.dg, inv);
       xd[0] = inv[0] * rd.r[0] + inv[1] * rd.r[1];
       xd[1] = inv[2] * rd.r[0] + inv[3] * rd.r[1];
       buf[tid] = xd[0]; buf[T + tid] = xd[1];
-      __syncthreads();
+      cta_sync<T>();
       if (tid > 0) { xl[0] = buf[tid - 1]; xl[1] = buf[T + tid - 1]; }
     }
     // ---- back-substitution of the own vertices, U -= dU ----------------------
@@ -742,7 +756,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       sA[i0 + 2] -= xc[0]; sq[i0 + 2] -= xc[1];
       sA[i0 + 3] -= xd[0]; sq[i0 + 3] -= xd[1];
     }
-    __syncthreads();
+    cta_sync<T>();
     ++it;
   }
   // update_solution (ar:247-251): Un <- U, into the other buffer
