@@ -315,3 +315,60 @@ def test_full_size_trees_short_horizon(order, Nx, Nt, steps):
     assert mism <= 0.01 * lj.size, (mism, lj.size)
     assert np.abs(jun[:, 0] - lj).max() <= 1
     assert int(an._dev.get_flags()[0]) & (1 | 8) == 0
+
+
+def test_per_network_inlet_tables():
+    """af_desc.q_ins_per_network = 1: every ensemble member has its own inlet
+    table; the batch must equal the members run one by one."""
+    from bloodflow_b200.engine import DeviceNetwork
+    from bloodflow_b200.arteryfe.artery_network import ArteryNetwork
+    from bloodflow_b200.synthetic import tree_param
+    d = ArteryNetwork(tree_param(3, Nx=48, Nt=600), _host_only=True)._description
+    scales = (1.0, 0.9, 1.15)
+
+    def make(q_ins, nb):
+        rep = lambda a: np.repeat(np.asarray(a)[None], nb, axis=0)          # noqa: E731
+        return DeviceNetwork(d['Nx'], d['Nt'], d['theta'], d['dt'], d['junctions'], d['leaves'],
+                             k1=d['k1'], k2=d['k2'], k3=d['k3'], rho=d['rho'], Re=d['Re'], db=d['db'], p0=d['p0'],
+                             Ru=rep(d['Ru']), Rd=rep(d['Rd']), L=rep(d['L']), q0=rep(d['q0']),
+                             R1=rep(d['R1']), R2=rep(d['R2']), CT=rep(d['CT']), q_ins=q_ins)
+    batch = make(np.array([d['q_ins'] * s for s in scales]), 3)
+    batch.step(0, 40)
+    A, q = batch.get_state()
+    for m, s in enumerate(scales):
+        one = make(d['q_ins'] * s, 1)
+        one.step(0, 40)
+        A1, q1 = one.get_state()
+        np.testing.assert_array_equal(A[m], A1[0])
+        np.testing.assert_array_equal(q[m], q1[0])
+    assert not np.array_equal(q[0], q[1])
+
+
+def test_tapered_vessels_in_a_batch():
+    """Coefficient tables (tapered vessels only) are per network and artery: a
+    batch of demo-like bifurcations with different tapers equals single runs,
+    including a member whose daughters are NOT tapered (mixed table slots)."""
+    from bloodflow_b200.engine import DeviceNetwork
+    from bloodflow_b200.arteryfe.artery_network import ArteryNetwork
+    import bloodflow_b200.arteryfe as af
+    d = ArteryNetwork(af.ParamParser(os.path.join(GOLDEN, 'golden_c1.cfg')), _host_only=True)._description
+    Rd = np.array([d['Rd'], d['Rd'] * np.array([1.0, 0.97, 1.02]), d['Ru']])      # member 2: untapered
+
+    def make(rows):
+        nb = len(rows)
+        rep = lambda a: np.repeat(np.asarray(a)[None], nb, axis=0)          # noqa: E731
+        return DeviceNetwork(d['Nx'], d['Nt'], d['theta'], d['dt'], d['junctions'], d['leaves'],
+                             k1=d['k1'], k2=d['k2'], k3=d['k3'], rho=d['rho'], Re=d['Re'], db=d['db'], p0=d['p0'],
+                             Ru=rep(d['Ru']), Rd=Rd[rows], L=rep(d['L']), q0=rep(d['q0']),
+                             R1=rep(d['R1']), R2=rep(d['R2']), CT=rep(d['CT']), q_ins=d['q_ins'])
+    batch = make([0, 1, 2])
+    batch.step(0, 30)
+    A, q = batch.get_state()
+    for m in range(3):
+        one = make([m])
+        one.step(0, 30)
+        A1, q1 = one.get_state()
+        np.testing.assert_array_equal(A[m], A1[0])
+        np.testing.assert_array_equal(q[m], q1[0])
+    assert not np.array_equal(A[0], A[1])
+    assert int(np.bitwise_or.reduce(batch.get_flags())) & 9 == 0
