@@ -54,6 +54,7 @@ PROTOTYPES = {
     'af_net_step': (c_int, [Handle, c_i64, c_i64]),
     'af_net_sync': (c_int, [Handle]),
     'af_net_set_store': (c_int, [Handle, P_u8, c_i32, c_i32, c_i32]),
+    'af_net_set_store_host': (c_int, [Handle, P_dbl, P_dbl, P_dbl, P_dbl]),
     'af_net_snapshot_count': (c_int, [Handle, P_i32]),
     'af_net_fetch_snapshots': (c_int, [Handle, P_dbl, P_dbl, P_dbl, P_dbl, P_i64]),
     'af_net_outlet_pressure_d': (c_int, [Handle, ctypes.POINTER(ctypes.c_void_p)]),

@@ -381,6 +381,7 @@ class ArteryNetwork(object):
         g = np.arange(total)
         n_snap = int(np.count_nonzero((g // Nt >= first_cycle) & (mask[g % Nt] != 0)))
         self._dev.set_store(mask, first_cycle, max(1, n_snap), fields)
+        self._dev.stream_store_to_host()         # snapshots leave the device while the loop runs
         self._dev.step(0, total)
         snaps = self._dev.fetch_snapshots()      # streams the snapshots out while the loop is still running
         self._dev.sync()

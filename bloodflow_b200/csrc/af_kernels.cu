@@ -953,6 +953,17 @@ struct af_net {
   std::vector<int64_t> snap_step;
   std::vector<cudaEvent_t> snap_event;   // recorded after the dump kernels of each snapshot
   cudaStream_t copy_stream = nullptr;    // snapshots are copied out while the time loop keeps running
+  // host destinations registered with af_net_set_store_host: af_net_step streams every snapshot
+  // through a small pinned ring (device -> pinned on copy_stream, pinned -> user buffer by the
+  // enqueueing host thread, which runs ahead of the GPU anyway)
+  double *h_flow = nullptr, *h_area = nullptr, *h_press = nullptr, *h_outlet = nullptr;
+  static const int kRing = 4;
+  double* ring = nullptr;                // pinned, kRing slots of slot_doubles
+  size_t slot_doubles = 0;
+  cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  int ring_snap[kRing] = {-1, -1, -1, -1};   // snapshot held by each slot (-1: free)
+  int n_streamed = 0;                    // snapshots whose device->pinned copy has been enqueued
+  int n_delivered = 0;                   // snapshots that have arrived in the user buffers
   // log
   int log_cap = 0, log_n = 0;
   // scratch for the fine-grained calls
@@ -1228,6 +1239,8 @@ extern "C" void af_net_destroy(af_net* n) {
   if (n->stream) cudaStreamSynchronize(n->stream);
   for (void* p : n->allocs) cudaFree(p);
   for (cudaEvent_t ev : n->snap_event) cudaEventDestroy(ev);
+  for (int k = 0; k < af_net::kRing; ++k) if (n->ring_done[k]) cudaEventDestroy(n->ring_done[k]);
+  if (n->ring) cudaFreeHost(n->ring);
   if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
   if (n->own_stream && n->stream) cudaStreamDestroy(n->stream);
   delete n;
@@ -1244,6 +1257,75 @@ extern "C" int af_net_sync(af_net* n) {
   if (rc) return rc;
   AF_CUDA(cudaStreamSynchronize(n->stream));
   AF_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
+// ---- streaming snapshots to host buffers -----------------------------------------------
+static size_t snapshot_doubles(const af_net* n) {
+  const NetDev& nd = n->nd;
+  size_t per = (size_t)nd.nb * nd.na * nd.np, pl = (size_t)nd.nb * nd.nl, d = 0;
+  if (n->fields & AF_STORE_FLOW) d += per;
+  if (n->fields & AF_STORE_AREA) d += per;
+  if (n->fields & AF_STORE_PRESSURE) d += per;
+  if (n->fields & AF_STORE_OUTLET_PRESSURE) d += pl;
+  return d;
+}
+
+// pinned slot -> user buffers (host memcpy); frees the slot
+static void deliver_slot(af_net* n, int slot) {
+  const NetDev& nd = n->nd;
+  const size_t per = (size_t)nd.nb * nd.na * nd.np, pl = (size_t)nd.nb * nd.nl;
+  const int i = n->ring_snap[slot];
+  const double* src = n->ring + (size_t)slot * n->slot_doubles;
+  if (n->fields & AF_STORE_FLOW) { if (n->h_flow) memcpy(n->h_flow + per * i, src, per * sizeof(double)); src += per; }
+  if (n->fields & AF_STORE_AREA) { if (n->h_area) memcpy(n->h_area + per * i, src, per * sizeof(double)); src += per; }
+  if (n->fields & AF_STORE_PRESSURE) { if (n->h_press) memcpy(n->h_press + per * i, src, per * sizeof(double)); src += per; }
+  if (n->fields & AF_STORE_OUTLET_PRESSURE) { if (n->h_outlet) memcpy(n->h_outlet + pl * i, src, pl * sizeof(double)); }
+  n->ring_snap[slot] = -1;
+  n->n_delivered++;
+}
+
+// Deliver finished copies; with `block` wait for the oldest one (ring full / final drain).
+static int drain_ring(af_net* n, bool block_oldest, bool all) {
+  for (;;) {
+    int oldest = -1;
+    for (int k = 0; k < af_net::kRing; ++k)
+      if (n->ring_snap[k] >= 0 && (oldest < 0 || n->ring_snap[k] < n->ring_snap[oldest])) oldest = k;
+    if (oldest < 0) return AF_OK;
+    cudaError_t q = cudaEventQuery(n->ring_done[oldest]);
+    if (q == cudaErrorNotReady) {
+      if (!block_oldest && !all) return AF_OK;
+      AF_CUDA(cudaEventSynchronize(n->ring_done[oldest]));
+    } else if (q != cudaSuccess) {
+      return fail(AF_ECUDA, cudaGetErrorString(q));
+    }
+    deliver_slot(n, oldest);
+    block_oldest = false;
+  }
+}
+
+// enqueue device -> pinned copies of snapshot i (gated on its event) into a free ring slot
+static int stream_snapshot(af_net* n, int i) {
+  const NetDev& nd = n->nd;
+  int slot = -1;
+  for (int k = 0; k < af_net::kRing; ++k)
+    if (n->ring_snap[k] < 0) { slot = k; break; }
+  if (slot < 0) {
+    int rc = drain_ring(n, true, false);
+    if (rc) return rc;
+    for (int k = 0; k < af_net::kRing; ++k)
+      if (n->ring_snap[k] < 0) { slot = k; break; }
+  }
+  const size_t per = (size_t)nd.nb * nd.na * nd.np, pl = (size_t)nd.nb * nd.nl;
+  double* dst = n->ring + (size_t)slot * n->slot_doubles;
+  AF_CUDA(cudaStreamWaitEvent(n->copy_stream, n->snap_event[i], 0));
+  if (n->fields & AF_STORE_FLOW) { AF_CUDA(cudaMemcpyAsync(dst, n->s_flow + per * i, per * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream)); dst += per; }
+  if (n->fields & AF_STORE_AREA) { AF_CUDA(cudaMemcpyAsync(dst, n->s_area + per * i, per * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream)); dst += per; }
+  if (n->fields & AF_STORE_PRESSURE) { AF_CUDA(cudaMemcpyAsync(dst, n->s_press + per * i, per * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream)); dst += per; }
+  if (n->fields & AF_STORE_OUTLET_PRESSURE) { AF_CUDA(cudaMemcpyAsync(dst, n->s_outlet + pl * i, pl * sizeof(double), cudaMemcpyDeviceToHost, n->copy_stream)); }
+  AF_CUDA(cudaEventRecord(n->ring_done[slot], n->copy_stream));
+  n->ring_snap[slot] = i;
+  n->n_streamed = i + 1;
   return AF_OK;
 }
 
@@ -1271,6 +1353,7 @@ static int take_snapshot(af_net* n, int64_t g) {
   AF_CUDA(cudaEventRecord(n->snap_event[n->n_snap], n->stream));
   n->snap_step.push_back(g);
   n->n_snap++;
+  if (n->ring) return stream_snapshot(n, n->n_snap - 1);
   return AF_OK;
 }
 
@@ -1285,6 +1368,10 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     int64_t cycle = g / Nt;
     if (n->max_snap && cycle >= n->first_cycle && n->mask[step]) {
       rc = take_snapshot(n, g);
+      if (rc) return rc;
+    }
+    if (n->ring && n->n_delivered < n->n_streamed && (g & 7) == 0) {
+      rc = drain_ring(n, false, false);
       if (rc) return rc;
     }
     int log_slot = (n->log_n < n->log_cap) ? n->log_n++ : -1;
@@ -1369,6 +1456,29 @@ extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t fir
   n->max_snap = max_snapshots;
   n->n_snap = 0;
   n->snap_step.clear();
+  n->n_streamed = n->n_delivered = 0;
+  n->h_flow = n->h_area = n->h_press = n->h_outlet = nullptr;
+  if (n->ring) { cudaFreeHost(n->ring); n->ring = nullptr; }
+  for (int k = 0; k < af_net::kRing; ++k) n->ring_snap[k] = -1;
+  return AF_OK;
+}
+
+extern "C" int af_net_set_store_host(af_net* n, double* flow, double* area, double* pressure,
+                                     double* outlet_pressure) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!n->max_snap) return fail(AF_ESTATE, "af_net_set_store first");
+  if (n->n_snap) return fail(AF_ESTATE, "snapshots already taken");
+  if (!n->copy_stream) AF_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+  n->h_flow = flow; n->h_area = area; n->h_press = pressure; n->h_outlet = outlet_pressure;
+  n->slot_doubles = snapshot_doubles(n);
+  if (n->ring) { cudaFreeHost(n->ring); n->ring = nullptr; }
+  AF_CUDA(cudaHostAlloc((void**)&n->ring, n->slot_doubles * af_net::kRing * sizeof(double), cudaHostAllocDefault));
+  for (int k = 0; k < af_net::kRing; ++k) {
+    if (!n->ring_done[k]) AF_CUDA(cudaEventCreateWithFlags(&n->ring_done[k], cudaEventDisableTiming));
+    n->ring_snap[k] = -1;
+  }
+  n->n_streamed = n->n_delivered = 0;
   return AF_OK;
 }
 
@@ -1387,6 +1497,16 @@ extern "C" int af_net_fetch_snapshots(af_net* n, double* flow, double* area, dou
   if (area && !n->s_area) return fail(AF_ESTATE, "area not stored");
   if (pressure && !n->s_press) return fail(AF_ESTATE, "pressure not stored");
   if (outlet_pressure && !n->s_outlet) return fail(AF_ESTATE, "outlet pressure not stored");
+  if (n->ring) {
+    // streaming mode: everything is already on its way to the registered host buffers
+    if ((flow && flow != n->h_flow) || (area && area != n->h_area) || (pressure && pressure != n->h_press) ||
+        (outlet_pressure && outlet_pressure != n->h_outlet))
+      return fail(AF_EINVAL, "streaming store: pass the buffers registered with af_net_set_store_host (or NULL)");
+    rc = drain_ring(n, false, true);
+    if (rc) return rc;
+    if (step) for (int i = 0; i < n->n_snap; ++i) step[i] = n->snap_step[i];
+    return AF_OK;
+  }
   if (!n->copy_stream) AF_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
   // Snapshot by snapshot on a second stream, each copy gated by the event recorded
   // after its dump kernels: the downloads overlap the rest of the enqueued time loop.

@@ -89,6 +89,25 @@ class DeviceNetwork(object):
         check(lib.af_net_set_store(self._h, mask.ctypes.data_as(_ffi.P_u8), int(first_cycle), int(max_snapshots),
                                    int(fields)))
         self._store_fields = int(fields)
+        self._host_store = None
+        self._max_snap = int(max_snapshots)
+
+    def stream_store_to_host(self):
+        """Allocate the host arrays of the configured store now and let af_net_step
+        stream every snapshot into them while the loop runs (af_net_set_store_host)."""
+        n = self._max_snap
+        out, ptrs = {}, []
+        for name, bit, shape in (('flow', _ffi.AF_STORE_FLOW, (n, self.nb, self.na, self.np)),
+                                 ('area', _ffi.AF_STORE_AREA, (n, self.nb, self.na, self.np)),
+                                 ('pressure', _ffi.AF_STORE_PRESSURE, (n, self.nb, self.na, self.np)),
+                                 ('outlet_pressure', _ffi.AF_STORE_OUTLET_PRESSURE, (n, self.nb, self.nl))):
+            if self._store_fields & bit:
+                out[name] = np.empty(shape)
+                ptrs.append(dptr(out[name]))
+            else:
+                ptrs.append(None)
+        check(lib.af_net_set_store_host(self._h, *ptrs))
+        self._host_store = out
 
     def snapshot_count(self):
         c = ctypes.c_int32(0)
@@ -97,6 +116,15 @@ class DeviceNetwork(object):
 
     def fetch_snapshots(self):
         n = self.snapshot_count()
+        if getattr(self, '_host_store', None) is not None:
+            hs = self._host_store
+            step = np.zeros(n, dtype=np.int64)
+            check(lib.af_net_fetch_snapshots(
+                self._h, *[dptr(hs[k]) if k in hs else None for k in ('flow', 'area', 'pressure', 'outlet_pressure')],
+                step.ctypes.data_as(_ffi.P_i64)))
+            out = {k: v[:n] for k, v in hs.items()}
+            out['step'] = step
+            return out
         out = {'step': np.zeros(n, dtype=np.int64)}
         ptrs = []
         for name, bit in (('flow', _ffi.AF_STORE_FLOW), ('area', _ffi.AF_STORE_AREA),

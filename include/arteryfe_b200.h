@@ -141,6 +141,12 @@ int af_net_sync(af_net* net);
  * AF_STORE_*.  Capacity `max_snapshots`; further dump steps are dropped. */
 int af_net_set_store(af_net* net, const uint8_t* step_mask, int32_t first_cycle, int32_t max_snapshots,
                      int32_t fields);
+/* Optional, after af_net_set_store: register HOST destinations (layouts as in
+ * af_net_fetch_snapshots; NULL to skip a field).  af_net_step then streams every
+ * snapshot out while the loop runs (device -> pinned ring on a second stream ->
+ * these buffers); af_net_fetch_snapshots with the same pointers only waits for the
+ * last ones.  The buffers must stay valid until then. */
+int af_net_set_store_host(af_net* net, double* flow, double* area, double* pressure, double* outlet_pressure);
 int af_net_snapshot_count(af_net* net, int32_t* count);
 /* Copy stored fields out; each of flow/area/pressure is
  * [count][n_networks][n_arteries][Nx+1] (NULL to skip), outlet_pressure is
