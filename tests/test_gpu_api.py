@@ -345,3 +345,30 @@ def test_fused_step_equals_two_kernel_step(monkeypatch):
     for a, b in zip(fused[4], plain[4]):
         np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(fused[5], plain[5])
+
+
+def test_streamed_store_equals_plain_fetch():
+    """af_net_set_store_host streams snapshots to host buffers while af_net_step
+    is still enqueueing (pinned ring of 4 slots, more snapshots than slots, the
+    loop issued in several calls); the result must equal the plain fetch."""
+    import bloodflow_b200.arteryfe as af
+    from bloodflow_b200 import _ffi
+    from bloodflow_b200.synthetic import tree_param
+
+    def run(stream):
+        an = af.ArteryNetwork(tree_param(3, Nx=64, Nt=400, Nt_store=50))
+        an.define_x()
+        dev = an._dev
+        fields = _ffi.AF_STORE_FLOW | _ffi.AF_STORE_PRESSURE | _ffi.AF_STORE_OUTLET_PRESSURE
+        dev.set_store(an.store_mask(), 0, 23, fields)
+        if stream:
+            dev.stream_store_to_host()
+        for first, n in ((0, 7), (7, 120), (127, 53)):
+            dev.step(first, n)
+        return dev.fetch_snapshots()
+
+    a, b = run(True), run(False)
+    assert len(a['step']) == 23 and list(a['step']) == list(b['step']) == [8 * k for k in range(23)]
+    for key in ('flow', 'pressure', 'outlet_pressure'):
+        np.testing.assert_array_equal(a[key], b[key])
+    assert 'area' not in a
