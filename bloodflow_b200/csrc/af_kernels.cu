@@ -496,6 +496,21 @@ __device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const CellCoef
                                               const double* sA, const double* sq, double* pa, double* pb,
                                               double* pc, double* lo) {
   const int tid = threadIdx.x, i0 = 4 * tid;
+  if (T == 32) {
+    // one-warp (ensemble) kernel: ONE copy of the cell routine, executed four times.
+    // With 16 independent one-warp CTAs per SM the instruction cache, not ILP, is
+    // what the cells compete for (profiles/r01_c5_ncu_full_summary.txt).
+    // regions are contiguous: lo | pa | pb | pc, cell k -> region (k + 1) % 4
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      CellInt ci = artery_cell<true>(c, ccu, tab, S, sA, sq, i0 + k);
+      double* r = lo + ((k + 1) & 3) * 10 * T;
+      r[0 * T + tid] = ci.Gl; r[1 * T + tid] = ci.Gr;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { r[(2 + m) * T + tid] = ci.JA[m]; r[(6 + m) * T + tid] = ci.Jq[m]; }
+    }
+    return;
+  }
   double* reg[4] = {pa, pb, pc, lo};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -533,9 +548,9 @@ __device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const doubl
   CellInt left, own;
   cell_zero(left);
   cell_zero(own);
+  double part = 0.0;
   if (tid > 0) load_cell_right_part(lo, T, tid - 1, left);     // last cell of the previous thread
   load_cell_left_part(pa, T, tid, own);
-  double part = 0.0;
   {
     Row ra;
     build_row<true>(c, i0, first, sA, sq, left, own, EA[0], Eq[0], ra);
