@@ -1002,6 +1002,14 @@ struct af_net {
     return AF_OK;
   }
   template <typename Tp>
+  void dfree(Tp** p) {
+    if (!*p) return;
+    auto it = std::find(allocs.begin(), allocs.end(), (void*)*p);
+    if (it != allocs.end()) allocs.erase(it);
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  template <typename Tp>
   int upload(Tp** p, const Tp* h, size_t n) {
     int rc = dalloc(p, n);
     if (rc) return rc;
@@ -1065,8 +1073,7 @@ static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_ind
     case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot, fused);
     case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot, fused);
     case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot, fused);
-    case 512: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused);
-    default: return launch_artery<1024>(n, ba0, count, inlet_index, log_slot, fused);
+    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused);
   }
 }
 
@@ -1096,7 +1103,11 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   if (d->abi_version != AF_ABI_VERSION) return fail(AF_EINVAL, "af_desc.abi_version mismatch");
   if (d->n_networks < 1 || d->n_arteries < 1 || d->Nx < 2 || d->Nt < 1 || d->n_junctions < 0 || d->n_leaves < 0)
     return fail(AF_EINVAL, "bad sizes in af_desc");
-  if (d->Nx + 1 > 4096) return fail(AF_EINVAL, "Nx+1 > 4096 vertices per artery is not supported");
+  // one CTA per artery, four vertices per thread, 48 doubles of shared memory per thread:
+  // 512 threads (196 KB) is the largest CTA that fits the 227 KB of an SM
+  if (d->Nx + 1 > 2048) return fail(AF_EINVAL, "Nx+1 > 2048 vertices per artery is not supported");
+  if (!(d->dt > 0.0)) return fail(AF_EINVAL, "af_desc.dt must be positive");
+  if (d->root_artery >= d->n_arteries) return fail(AF_EINVAL, "root_artery out of range");
   if (!d->k1 || !d->k2 || !d->k3 || !d->rho || !d->Re || !d->db || !d->p0 || !d->Ru || !d->Rd || !d->L || !d->q0 ||
       !d->q_ins || (d->n_leaves && (!d->R1 || !d->R2 || !d->CT || !d->leaf_artery)) ||
       (d->n_junctions && (!d->junction_parent || !d->junction_d1 || !d->junction_d2)))
@@ -1136,6 +1147,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   for (int l = 0; l < nd.nl; ++l) {
     int a = d->leaf_artery[l];
     if (a < 0 || a >= nd.na) { af_net_destroy(n); return fail(AF_EINVAL, "leaf_artery out of range"); }
+    if (art_leaf[a] >= 0) { af_net_destroy(n); return fail(AF_EINVAL, "leaf_artery lists an artery twice"); }
     art_leaf[a] = l;
   }
   for (int j = 0; j < nd.nj; ++j) {
@@ -1145,9 +1157,16 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   }
   std::vector<int> art_jin(nd.na, -1), art_role(nd.na, 0), art_jout(nd.na, -1);
   for (int j = 0; j < nd.nj; ++j) {
-    art_jout[d->junction_parent[j]] = j;
-    art_jin[d->junction_d1[j]] = j; art_role[d->junction_d1[j]] = 1;
-    art_jin[d->junction_d2[j]] = j; art_role[d->junction_d2[j]] = 2;
+    const int p = d->junction_parent[j], d1 = d->junction_d1[j], d2 = d->junction_d2[j];
+    // every end of an artery carries exactly one boundary condition per step (an:767-786)
+    if (p == d1 || p == d2 || d1 == d2 || art_jout[p] >= 0 || art_jin[d1] >= 0 || art_jin[d2] >= 0 ||
+        art_leaf[p] >= 0 || d1 == nd.root_artery || d2 == nd.root_artery) {
+      af_net_destroy(n);
+      return fail(AF_EINVAL, "inconsistent topology: an artery end is claimed by more than one junction/outlet/inlet");
+    }
+    art_jout[p] = j;
+    art_jin[d1] = j; art_role[d1] = 1;
+    art_jin[d2] = j; art_role[d2] = 2;
   }
   int *dp, *dd1, *dd2, *dla, *dal, *djin, *drole, *djout;
   AF_TRY(n->upload(&dp, d->junction_parent, nd.nj));
@@ -1225,15 +1244,17 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
     if ((a != 0 && art_jin[a] < 0) || (art_leaf[a] < 0 && art_jout[a] < 0)) n->fused = false;
   if (const char* env = getenv("AF_NO_FUSE")) if (atoi(env)) n->fused = false;
   if (const char* env = getenv("AF_NO_PDL")) if (atoi(env)) n->pdl = false;
-  if (const char* env = getenv("AF_BOUNDARY_BLOCK")) n->boundary_block = atoi(env);
+  if (const char* env = getenv("AF_BOUNDARY_BLOCK")) {
+    int v = atoi(env);
+    if (v >= 32 && v <= 1024 && v % 32 == 0) n->boundary_block = v;
+  }
   cudaError_t e;
   switch (n->artery_threads) {
     case 32: e = prepare_artery<32>(n); break;
     case 64: e = prepare_artery<64>(n); break;
     case 128: e = prepare_artery<128>(n); break;
     case 256: e = prepare_artery<256>(n); break;
-    case 512: e = prepare_artery<512>(n); break;
-    default: e = prepare_artery<1024>(n); break;
+    default: e = prepare_artery<512>(n); break;
   }
   if (e != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("artery kernel smem: ") + cudaGetErrorString(e)); }
 
@@ -1455,7 +1476,11 @@ extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t fir
   // (re)configuration: buffers are reused when they are large enough
   if (fields != n->fields || max_snapshots > n->snap_cap) {
     size_t per = (size_t)nd.nb * nd.na * nd.np;
-    n->s_flow = n->s_area = n->s_press = n->s_outlet = nullptr;
+    // nothing may still be reading the old buffers (enqueued dumps, snapshot downloads)
+    AF_CUDA(cudaStreamSynchronize(n->stream));
+    if (n->copy_stream) AF_CUDA(cudaStreamSynchronize(n->copy_stream));
+    for (double** b : {&n->s_flow, &n->s_area, &n->s_press, &n->s_outlet}) n->dfree(b);
+    n->snap_cap = 0;
     if (fields & AF_STORE_FLOW) { rc = n->dalloc(&n->s_flow, per * max_snapshots); if (rc) return rc; }
     if (fields & AF_STORE_AREA) { rc = n->dalloc(&n->s_area, per * max_snapshots); if (rc) return rc; }
     if (fields & AF_STORE_PRESSURE) { rc = n->dalloc(&n->s_press, per * max_snapshots); if (rc) return rc; }
@@ -1473,7 +1498,11 @@ extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t fir
   n->snap_step.clear();
   n->n_streamed = n->n_delivered = 0;
   n->h_flow = n->h_area = n->h_press = n->h_outlet = nullptr;
-  if (n->ring) { cudaFreeHost(n->ring); n->ring = nullptr; }
+  if (n->ring) {
+    if (n->copy_stream) AF_CUDA(cudaStreamSynchronize(n->copy_stream));   // undelivered copies are dropped
+    cudaFreeHost(n->ring);
+    n->ring = nullptr;
+  }
   for (int k = 0; k < af_net::kRing; ++k) n->ring_snap[k] = -1;
   return AF_OK;
 }
@@ -1487,7 +1516,11 @@ extern "C" int af_net_set_store_host(af_net* n, double* flow, double* area, doub
   if (!n->copy_stream) AF_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
   n->h_flow = flow; n->h_area = area; n->h_press = pressure; n->h_outlet = outlet_pressure;
   n->slot_doubles = snapshot_doubles(n);
-  if (n->ring) { cudaFreeHost(n->ring); n->ring = nullptr; }
+  if (n->ring) {
+    AF_CUDA(cudaStreamSynchronize(n->copy_stream));
+    cudaFreeHost(n->ring);
+    n->ring = nullptr;
+  }
   AF_CUDA(cudaHostAlloc((void**)&n->ring, n->slot_doubles * af_net::kRing * sizeof(double), cudaHostAllocDefault));
   for (int k = 0; k < af_net::kRing; ++k) {
     if (!n->ring_done[k]) AF_CUDA(cudaEventCreateWithFlags(&n->ring_done[k], cudaEventDisableTiming));

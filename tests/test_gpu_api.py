@@ -372,3 +372,62 @@ def test_streamed_store_equals_plain_fetch():
     for key in ('flow', 'pressure', 'outlet_pressure'):
         np.testing.assert_array_equal(a[key], b[key])
     assert 'area' not in a
+
+
+def _raw_network(junctions, leaves, na=3, Nx=16, root_artery=0, **kw):
+    from bloodflow_b200.engine import DeviceNetwork
+    ones = np.ones(na)
+    return DeviceNetwork(Nx, 8, 1.0, 1e-3, junctions, leaves, k1=2e7, k2=-22.5, k3=8.65e5, rho=1.0, Re=100.0,
+                         db=1.0, p0=1.0, Ru=0.4 * ones, Rd=0.4 * ones, L=5 * ones, q0=ones,
+                         R1=np.ones(len(leaves)), R2=np.ones(len(leaves)), CT=np.ones(len(leaves)),
+                         q_ins=np.ones(8), root_artery=root_artery, **kw)
+
+
+@pytest.mark.parametrize('junctions,leaves,root', [
+    ([[0, 1, 1]], [1, 2], 0),                 # the same daughter twice
+    ([[0, 1, 2], [0, 1, 2]], [1, 2], 0),      # two junctions on the same ends
+    ([[0, 1, 2]], [0, 1, 2], 0),              # a parent that is also an outlet
+    ([[0, 1, 2]], [1, 1], 0),                 # an outlet listed twice
+    ([[1, 0, 2]], [0, 2], 0),                 # the root as a daughter
+    ([[0, 1, 2]], [1, 2], 3),                 # root index outside the network
+    ([[0, 1, 7]], [1, 2], 0),                 # index out of range
+])
+def test_inconsistent_topologies_are_rejected(junctions, leaves, root):
+    from bloodflow_b200 import _ffi
+    with pytest.raises(_ffi.AfError) as e:
+        _raw_network(junctions, leaves, root_artery=root)
+    assert e.value.code == _ffi.AF_EINVAL
+
+
+def test_size_limits():
+    from bloodflow_b200 import _ffi
+    net = _raw_network([[0, 1, 2]], [1, 2], Nx=2047)      # 2048 vertices: the largest CTA (512 threads)
+    net.step(0, 2)
+    net.sync()
+    A, q = net.get_state()
+    assert np.isfinite(A).all() and np.isfinite(q).all()
+    net.close()
+    with pytest.raises(_ffi.AfError):
+        _raw_network([[0, 1, 2]], [1, 2], Nx=2048)
+    with pytest.raises(_ffi.AfError):
+        _raw_network([[0, 1, 2]], [1, 2], Nx=1)
+
+
+def test_store_reconfiguration_does_not_accumulate_device_memory():
+    import torch
+    from bloodflow_b200 import _ffi
+    net = _raw_network([[0, 1, 2]], [1, 2], Nx=1023)
+    mask = np.ones(8, dtype=np.uint8)
+    fields = _ffi.AF_STORE_FLOW | _ffi.AF_STORE_AREA | _ffi.AF_STORE_PRESSURE
+    net.set_store(mask, 0, 4096, fields)                  # 3 x 4096 x 3 x 1024 x 8 B = 302 MB
+    net.step(0, 3)
+    first = net.fetch_snapshots()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for cap in (4097, 4098, 4099, 4100):
+        net.set_store(mask, 0, cap, fields)
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < 64 << 20                       # the old buffers were released, not kept
+    net.step(3, 2)
+    again = net.fetch_snapshots()
+    assert list(first['step']) == [0, 1, 2] and list(again['step']) == [3, 4]
+    net.close()
