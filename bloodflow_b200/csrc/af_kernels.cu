@@ -467,7 +467,23 @@ __device__ __forceinline__ Elim unpark(const double* base, int T, int t) {
   return e;
 }
 
-template <bool JAC>
+// The iterate U lives in shared memory with the four vertices of a thread in four
+// planes: vertex i at [(i & 3) * T + (i >> 2)].  A warp reading "its" vertex k (or
+// the neighbouring thread's) touches 32 consecutive doubles: no bank conflicts
+// (the natural order, stride 4 doubles per thread, is a 4-way conflict on every
+// access -- 0.96 M conflicts per launch in profiles/r01_final_ncu_full_summary.txt).
+template <int T>
+__device__ __forceinline__ int vix(int i) { return (i & 3) * T + (i >> 2); }
+
+template <int T>
+__device__ __forceinline__ void row_of(const ArteryCtx& c, int i, bool first, const double* sA, const double* sq,
+                                       const CellInt& left, const CellInt& own, double& EA, double& Eq, Row& row) {
+  // a neighbour that does not exist is replaced by the vertex itself (build_row ignores it)
+  const int jm = vix<T>(i > 0 ? i - 1 : i), j0 = vix<T>(i), jp = vix<T>(i < 4 * T - 1 ? i + 1 : i);
+  build_row<true>(c, i, first, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], left, own, EA, Eq, row);
+}
+
+template <int T, bool JAC>
 __device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
                                                const double* sA, const double* sq, int i) {
   CellInt ci;
@@ -482,7 +498,8 @@ __device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const CellCoe
         cc.t3[g] = tab[(6 + g) * S + i];
       }
     }
-    ci = cell_integrals<JAC>(c.h, c.Kr, cc, sA[i], sA[i + 1], sq[i], sq[i + 1]);
+    const int jl = vix<T>(i), jr = vix<T>(i + 1);
+    ci = cell_integrals<JAC>(c.h, c.Kr, cc, sA[jl], sA[jr], sq[jl], sq[jr]);
   }
   return ci;
 }
@@ -503,7 +520,7 @@ __device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const CellCoef
     // regions are contiguous: lo | pa | pb | pc, cell k -> region (k + 1) % 4
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-      CellInt ci = artery_cell<true>(c, ccu, tab, S, sA, sq, i0 + k);
+      CellInt ci = artery_cell<T, true>(c, ccu, tab, S, sA, sq, i0 + k);
       double* r = lo + ((k + 1) & 3) * 10 * T;
       r[0 * T + tid] = ci.Gl; r[1 * T + tid] = ci.Gr;
 #pragma unroll
@@ -514,7 +531,7 @@ __device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const CellCoef
   double* reg[4] = {pa, pb, pc, lo};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    CellInt ci = artery_cell<true>(c, ccu, tab, S, sA, sq, i0 + k);
+    CellInt ci = artery_cell<T, true>(c, ccu, tab, S, sA, sq, i0 + k);
     double* r = reg[k];
     r[0 * T + tid] = ci.Gl; r[1 * T + tid] = ci.Gr;
 #pragma unroll
@@ -553,11 +570,11 @@ __device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const doubl
   load_cell_left_part(pa, T, tid, own);
   {
     Row ra;
-    build_row<true>(c, i0, first, sA, sq, left, own, EA[0], Eq[0], ra);
+    row_of<T>(c, i0, first, sA, sq, left, own, EA[0], Eq[0], ra);
     part += ra.r[0] * ra.r[0] + ra.r[1] * ra.r[1];
     load_cell_right_part(pa, T, tid, left);
     load_cell_left_part(pb, T, tid, own);
-    build_row<true>(c, i0 + 1, first, sA, sq, left, own, EA[1], Eq[1], rb);
+    row_of<T>(c, i0 + 1, first, sA, sq, left, own, EA[1], Eq[1], rb);
     part += rb.r[0] * rb.r[0] + rb.r[1] * rb.r[1];
     Elim ea = make_elim(ra);
     park(pa, T, tid, ea);
@@ -567,11 +584,11 @@ __device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const doubl
     Row rc;
     load_cell_right_part(pb, T, tid, left);
     load_cell_left_part(pc, T, tid, own);
-    build_row<true>(c, i0 + 2, first, sA, sq, left, own, EA[2], Eq[2], rc);
+    row_of<T>(c, i0 + 2, first, sA, sq, left, own, EA[2], Eq[2], rc);
     part += rc.r[0] * rc.r[0] + rc.r[1] * rc.r[1];
     load_cell_right_part(pc, T, tid, left);
     load_cell_left_part(lo, T, tid, own);
-    build_row<true>(c, i0 + 3, first, sA, sq, left, own, EA[3], Eq[3], rd);
+    row_of<T>(c, i0 + 3, first, sA, sq, left, own, EA[3], Eq[3], rd);
     part += rd.r[0] * rd.r[0] + rd.r[1] * rd.r[1];
     Elim ec = make_elim(rc);
     park(pc, T, tid, ec);
@@ -607,10 +624,22 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
     // U <- Un (ar:158; the Newton initial guess is the previous solution)
     const double* gA = nd.A[cur] + off;
     const double* gq = nd.q[cur] + off;
-    for (int i = tid; i < NV; i += T) {
-      sA[i] = i < np ? gA[i] : 1.0;
-      sq[i] = i < np ? gq[i] : 0.0;
+    // each thread fetches its own four vertices (two 16-byte loads per field: a warp
+    // reads 1 KB contiguously); the rows of an artery start 256-byte aligned
+    const int i0 = 4 * tid;
+    double va[4] = {1.0, 1.0, 1.0, 1.0}, vq[4] = {0.0, 0.0, 0.0, 0.0};     // padding vertices
+    if (i0 + 3 < np) {
+      const double2 a01 = *reinterpret_cast<const double2*>(gA + i0), a23 = *reinterpret_cast<const double2*>(gA + i0 + 2);
+      const double2 q01 = *reinterpret_cast<const double2*>(gq + i0), q23 = *reinterpret_cast<const double2*>(gq + i0 + 2);
+      va[0] = a01.x; va[1] = a01.y; va[2] = a23.x; va[3] = a23.y;
+      vq[0] = q01.x; vq[1] = q01.y; vq[2] = q23.x; vq[3] = q23.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k < np) { va[k] = gA[i0 + k]; vq[k] = gq[i0 + k]; }
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sA[k * T + tid] = va[k]; sq[k * T + tid] = vq[k]; }
   }
   ArteryCtx c;
   c.ne = ne; c.np = np;
@@ -683,7 +712,6 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   for (int g = 0; g < 3; ++g) { ccu.c1[g] = c.c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
   const int slot = nd.coef_slot[ba];
   const double* tab = slot >= 0 ? nd.cellcoef + (size_t)slot * 9 * S : nullptr;
-  const int i0 = 4 * tid;
   double EA[4], Eq[4];          // explicit part of the residual of the own vertices
   cta_sync<T>();
 
@@ -766,10 +794,10 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       back_sub(unpark(pb, T, tid), xl, xd, xb);
       back_sub(unpark(pa, T, tid), xl, xb, xa);
       back_sub(unpark(pc, T, tid), xb, xd, xc);
-      sA[i0] -= xa[0]; sq[i0] -= xa[1];
-      sA[i0 + 1] -= xb[0]; sq[i0 + 1] -= xb[1];
-      sA[i0 + 2] -= xc[0]; sq[i0 + 2] -= xc[1];
-      sA[i0 + 3] -= xd[0]; sq[i0 + 3] -= xd[1];
+      sA[tid] -= xa[0]; sq[tid] -= xa[1];
+      sA[T + tid] -= xb[0]; sq[T + tid] -= xb[1];
+      sA[2 * T + tid] -= xc[0]; sq[2 * T + tid] -= xc[1];
+      sA[3 * T + tid] -= xd[0]; sq[3 * T + tid] -= xd[1];
     }
     cta_sync<T>();
     ++it;
@@ -778,7 +806,17 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
   {
     double* gA = nd.A[cur ^ 1] + off;
     double* gq = nd.q[cur ^ 1] + off;
-    for (int i = tid; i < np; i += T) { gA[i] = sA[i]; gq[i] = sq[i]; }
+    const int i0 = 4 * tid;
+    if (i0 + 3 < np) {
+      *reinterpret_cast<double2*>(gA + i0) = make_double2(sA[tid], sA[T + tid]);
+      *reinterpret_cast<double2*>(gA + i0 + 2) = make_double2(sA[2 * T + tid], sA[3 * T + tid]);
+      *reinterpret_cast<double2*>(gq + i0) = make_double2(sq[tid], sq[T + tid]);
+      *reinterpret_cast<double2*>(gq + i0 + 2) = make_double2(sq[2 * T + tid], sq[3 * T + tid]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k < np) { gA[i0 + k] = sA[k * T + tid]; gq[i0 + k] = sq[k * T + tid]; }
+    }
   }
   if (tid == 0) {
     nd.art_its[ba] = it;

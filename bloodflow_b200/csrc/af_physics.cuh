@@ -896,12 +896,14 @@ AF_HD void row_identity(Row& w) {
 
 // Newton row of vertex i (residual + 2x2 blocks, Dirichlet rows applied) from
 // the right part of cell i-1 (Gr, JA[2..3], Jq[2..3] in `left`) and the left
-// part of cell i (Gl, JA[0..1], Jq[0..1] in `own`).  sA/sq: the iterate U.
+// part of cell i (Gl, JA[0..1], Jq[0..1] in `own`).  (Am,qm), (Ai,qi), (Ap,qp): the
+// iterate U at vertices i-1, i, i+1 (anything where the vertex does not exist).
 // On the first pass (U == Un) the explicit part E of the residual is produced,
 // afterwards it is consumed.  Vertices i >= np are padding (identity rows).
 template <bool JAC>
-AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* sA, const double* sq,
-                     const CellInt& left, const CellInt& own, double& EA, double& Eq, Row& row) {
+AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, double Am, double qm, double Ai, double qi,
+                     double Ap, double qp, const CellInt& left, const CellInt& own, double& EA, double& Eq,
+                     Row& row) {
   if (i >= c.np) {
     row_identity(row);
     return;
@@ -910,12 +912,11 @@ AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* s
   const bool end = (i == 0 || i == ne);
   double fF2 = 0.0, fdA = 0.0, fdq = 0.0;
   if (end) {
-    PointTerms ft = facet_terms<JAC>(i == 0 ? c.c1_0 : c.c1_L, sA[i], sq[i]);
+    PointTerms ft = facet_terms<JAC>(i == 0 ? c.c1_0 : c.c1_L, Ai, qi);
     fF2 = ft.F2;
     if (JAC) { fdA = ft.dF2dA; fdq = ft.dF2dq; }
   }
-  VertexX vx = vertex_x(i, ne, c.h, i > 0 ? sA[i - 1] : 0.0, i > 0 ? sq[i - 1] : 0.0, sA[i], sq[i],
-                        i < ne ? sA[i + 1] : 0.0, i < ne ? sq[i + 1] : 0.0, left.Gr, own.Gl, fF2);
+  VertexX vx = vertex_x(i, ne, c.h, Am, qm, Ai, qi, Ap, qp, left.Gr, own.Gl, fF2);
   if (first_pass) {
     EA = -vx.mA + c.dte * vx.XA;
     Eq = -vx.mq + c.dte * vx.Xq;
@@ -933,12 +934,12 @@ AF_HD void build_row(const ArteryCtx& c, int i, bool first_pass, const double* s
     const bool fixq = (i == 0) ? true : !c.leaf;
     const double gA = (i == 0) ? c.gAin : c.gAout, gq = (i == 0) ? c.gqin : c.gqout;
     if (fixA) {
-      row.r[0] = sA[i] - gA;
+      row.r[0] = Ai - gA;
       row.dg[0] = 1.0; row.dg[1] = 0.0;
       row.lo[0] = row.lo[1] = row.up[0] = row.up[1] = 0.0;
     }
     if (fixq) {
-      row.r[1] = sq[i] - gq;
+      row.r[1] = qi - gq;
       row.dg[2] = 0.0; row.dg[3] = 1.0;
       row.lo[2] = row.lo[3] = row.up[2] = row.up[3] = 0.0;
     }

@@ -152,7 +152,9 @@ int hh_artery_solve(const double* vp, int Nx, double dt, double theta, double* A
       cell_zero(left);
       if (i > 0) left = cell(i - 1);
       CellInt own = cell(i);
-      build_row<true>(c, i, first, sA.data(), sq.data(), left, own, EA[i], Eq[i], rows[i]);
+      build_row<true>(c, i, first, i > 0 ? sA[i - 1] : 0.0, i > 0 ? sq[i - 1] : 0.0, sA[i], sq[i],
+                      i + 1 < (int)sA.size() ? sA[i + 1] : 0.0, i + 1 < (int)sq.size() ? sq[i + 1] : 0.0, left, own,
+                      EA[i], Eq[i], rows[i]);
       part += rows[i].r[0] * rows[i].r[0] + rows[i].r[1] * rows[i].r[1];
       if (first && i < np) {
         if (Rout) { Rout[2 * i] = rows[i].r[0]; Rout[2 * i + 1] = rows[i].r[1]; }
