@@ -26,6 +26,39 @@ namespace af {
 #define af_rsqrt(x) (1.0 / sqrt(x))
 #endif
 
+// Branch-free reciprocal and reciprocal square root for the artery kernel: the
+// hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-23) refined to ~1 ulp in straight-line
+// FMAs.  The library versions guard every call with a slow-path branch for denormal /
+// huge arguments, which cuts the assembly of a cell into a dozen small basic blocks;
+// areas and 2x2 block determinants are O(1) numbers, and 0 / negative / non-finite
+// arguments still come out as inf / NaN and are caught by the Newton loop's
+// non-finite test.  Host builds (tests/host_harness) use the plain expressions.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double af_rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);             // e + e^2: one cubic step, 2^-23 -> 2^-69
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);          // clean-up step to ~1 ulp
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double af_rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double t = x * y;
+  double e = fma(-t, y, 1.0);                   // 1 - x y^2
+  double p = fma(0.375, e, 0.5) * e;            // e/2 + 3 e^2/8: cubic step, 2^-23 -> 2^-67
+  y = fma(y, p, y);
+  t = x * y;
+  e = fma(-t, y, 1.0);
+  return fma(0.5 * y, e, y);                    // clean-up step to ~1 ulp
+}
+#else
+inline double af_rcp_fast(double x) { return 1.0 / x; }
+inline double af_rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+#endif
+
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSqrtPi = 1.7724538509055159;   // == (double)sqrt((double)pi)
 constexpr double kDolfinEps = 3.0e-16;           // [3P] DOLFIN_EPS
@@ -742,7 +775,7 @@ struct PointTerms {
 template <bool JAC>
 AF_HD PointTerms point_terms(double A, double q, double c1, double t2, double t3, double Kr) {
   PointTerms t;
-  double isA = af_rsqrt(A);
+  double isA = af_rsqrt_fast(A);
   double sA = A * isA;
   double inv = isA * isA;
   double qi = q * inv;
@@ -971,7 +1004,7 @@ AF_HD void mul2(const double a[4], const double b[4], double o[4]) {
 }
 
 AF_HD void inv2v(const double d[4], double o[4]) {
-  double r = 1.0 / (d[0] * d[3] - d[1] * d[2]);
+  double r = af_rcp_fast(d[0] * d[3] - d[1] * d[2]);
   o[0] = d[3] * r; o[1] = -d[1] * r; o[2] = -d[2] * r; o[3] = d[0] * r;
 }
 
