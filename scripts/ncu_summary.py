@@ -1,0 +1,44 @@
+"""Condense an `ncu --set full` report into the few lines kept under profiles/.
+
+usage: python scripts/ncu_summary.py report.ncu-rep > profiles/rNN_..._summary.txt
+(reads the report with `ncu -i ... --page raw --csv`; no GPU needed)"""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = (
+    'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+    'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+    'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+    'sm__cycles_elapsed.max', 'smsp__cycles_active.avg', 'launch__grid_size', 'launch__block_size',
+    'launch__shared_mem_per_block_dynamic',
+)
+STALL = 'smsp__average_warps_issue_stalled_'
+
+
+def main(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], check=True, capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    head, units, body = rows[0], rows[1], rows[2:]
+    col = {name: k for k, name in enumerate(head)}
+    for r in body:
+        print('== %s' % r[col['Kernel Name']])
+        for m in KEEP:
+            if m in col:
+                print('   %s %s %s' % (m, r[col[m]], units[col[m]]))
+        stalls = []
+        for name, k in col.items():
+            if name.startswith(STALL) and name.endswith('_per_issue_active.ratio'):
+                try:
+                    stalls.append((float(r[k]), name[len(STALL):-len('_per_issue_active.ratio')]))
+                except ValueError:
+                    pass
+        stalls.sort(reverse=True)
+        print('   stalls: ' + ', '.join('%s=%.2f' % (n, v) for v, n in stalls[:7]))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
