@@ -11,3 +11,10 @@ CPU fallback: importing ``bloodflow_b200._ffi`` without the built library, or
 creating a network without a CUDA device, raises.
 """
 __version__ = "0.1.0"
+
+
+def release_cached_memory():
+    """Return the device / pinned blocks cached by the library to the driver
+    (af_release_cached_memory; the analogue of torch.cuda.empty_cache)."""
+    from . import _ffi
+    _ffi.check(_ffi.lib.af_release_cached_memory())

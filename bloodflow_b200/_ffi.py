@@ -51,6 +51,7 @@ PROTOTYPES = {
     'af_desc_defaults': (None, [ctypes.POINTER(AfDesc)]),
     'af_net_create': (c_int, [ctypes.POINTER(AfDesc), ctypes.POINTER(Handle)]),
     'af_net_destroy': (None, [Handle]),
+    'af_release_cached_memory': (c_int, []),
     'af_net_step': (c_int, [Handle, c_i64, c_i64]),
     'af_net_sync': (c_int, [Handle]),
     'af_net_set_store': (c_int, [Handle, P_u8, c_i32, c_i32, c_i32]),

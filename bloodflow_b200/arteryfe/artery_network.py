@@ -11,6 +11,8 @@ same device code the time loop uses, one call at a time.
 import configparser
 import os
 
+import copy
+
 import numpy as np
 
 from .. import _ffi
@@ -46,6 +48,10 @@ class ArteryNetwork(object):
         with ``.param``, ``.geo``, ``.solution`` dicts).  ``wk_scale`` overrides
         the two hard-coded Windkessel factors of HEAD (0.3, 0.01); it can also
         be given as ``R1_factor`` / ``R2_factor`` in the [Solution] section."""
+        # the reference overwrites param.param['Ru'/'Rd'/'L'/'R1'/...] in place (an:66-70), which
+        # breaks a second ArteryNetwork built from the same ParamParser; work on a copy instead
+        param = copy.copy(param)
+        param.param = dict(param.param)
         order = param.param['order']
         self.N = 2 ** order - 1
         self.device = device

@@ -15,6 +15,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -992,13 +994,71 @@ static int fail(int code, const std::string& msg) {
     }                                                                                          \
   } while (0)
 
+// ---- block cache -------------------------------------------------------------------
+// Device and pinned-host blocks released by a handle are kept (up to a cap) and handed
+// to the next request of exactly the same size.  Parameter sweeps and ensembles create
+// and destroy same-shaped networks in a loop; cudaMalloc / cudaFree / cudaHostAlloc of
+// the state and the snapshot store cost as much as ~1000 time steps of the order-8 tree
+// (scripts/e2e_breakdown.py).  AF_CACHE_MB caps the cached device bytes (default 4096,
+// 0 disables both caches); af_release_cached_memory() empties them.
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> dev;    // (device, bytes) -> block
+  std::multimap<size_t, void*> host;                   // pinned
+  size_t dev_bytes = 0, host_bytes = 0;
+  size_t dev_cap = (size_t)4096 << 20, host_cap = (size_t)512 << 20;
+  BlockCache() {
+    if (const char* env = getenv("AF_CACHE_MB")) {
+      long long mb = atoll(env);
+      dev_cap = mb > 0 ? (size_t)mb << 20 : 0;
+      if (mb <= 0) host_cap = 0;
+    }
+  }
+  void* take_dev(int device, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = dev.find({device, bytes});
+    if (it == dev.end()) return nullptr;
+    void* p = it->second;
+    dev.erase(it);
+    dev_bytes -= bytes;
+    return p;
+  }
+  bool give_dev(int device, size_t bytes, void* p) {     // false: not kept, caller frees
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev_bytes + bytes > dev_cap) return false;
+    dev.insert({{device, bytes}, p});
+    dev_bytes += bytes;
+    return true;
+  }
+  void* take_host(size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = host.find(bytes);
+    if (it == host.end()) return nullptr;
+    void* p = it->second;
+    host.erase(it);
+    host_bytes -= bytes;
+    return p;
+  }
+  bool give_host(size_t bytes, void* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (host_bytes + bytes > host_cap) return false;
+    host.insert({bytes, p});
+    host_bytes += bytes;
+    return true;
+  }
+};
+static BlockCache& cache() {
+  static BlockCache* c = new BlockCache();     // never destroyed: no CUDA calls at process exit
+  return *c;
+}
+
 struct af_net {
   NetDev nd;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int cur = 0;
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;   // device blocks and their sizes in bytes
   // store
   std::vector<uint8_t> mask;
   int first_cycle = 0, max_snap = 0, fields = 0, n_snap = 0, snap_cap = 0;
@@ -1032,20 +1092,56 @@ struct af_net {
 
   template <typename Tp>
   int dalloc(Tp** p, size_t n) {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(Tp));
-    if (e != cudaSuccess) return fail(AF_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    allocs.push_back(q);
+    const size_t bytes = (((n ? n : 1) * sizeof(Tp)) + 511) & ~(size_t)511;
+    void* q = cache().take_dev(device, bytes);
+    if (q) {
+      // a recycled block holds the previous owner's data; small ones are cleared like the
+      // zero pages a fresh cudaMalloc hands out in practice, the bulk buffers (state, store)
+      // are always written before they are read
+      if (bytes <= ((size_t)1 << 20)) cudaMemsetAsync(q, 0, bytes, stream);
+    } else {
+      cudaError_t e = cudaMalloc(&q, bytes);
+      if (e == cudaErrorMemoryAllocation) {           // give the cached blocks back and retry once
+        cudaGetLastError();
+        af_release_cached_memory();
+        e = cudaMalloc(&q, bytes);
+      }
+      if (e != cudaSuccess) return fail(AF_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    allocs.push_back({q, bytes});
     *p = (Tp*)q;
     return AF_OK;
+  }
+  // the caller guarantees that no enqueued work still uses the block
+  static void release_block(int device, void* q, size_t bytes) {
+    if (!cache().give_dev(device, bytes, q)) cudaFree(q);
   }
   template <typename Tp>
   void dfree(Tp** p) {
     if (!*p) return;
-    auto it = std::find(allocs.begin(), allocs.end(), (void*)*p);
-    if (it != allocs.end()) allocs.erase(it);
-    cudaFree(*p);
+    for (auto it = allocs.begin(); it != allocs.end(); ++it)
+      if (it->first == (void*)*p) {
+        release_block(device, it->first, it->second);
+        allocs.erase(it);
+        break;
+      }
     *p = nullptr;
+  }
+  size_t ring_bytes = 0;
+  int ring_alloc(size_t bytes) {
+    ring = (double*)cache().take_host(bytes);
+    if (!ring) {
+      cudaError_t e = cudaHostAlloc((void**)&ring, bytes, cudaHostAllocDefault);
+      if (e != cudaSuccess) { ring = nullptr; return fail(AF_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    }
+    ring_bytes = bytes;
+    return AF_OK;
+  }
+  void ring_free() {          // the caller guarantees that no copy into the ring is in flight
+    if (!ring) return;
+    if (!cache().give_host(ring_bytes, ring)) cudaFreeHost(ring);
+    ring = nullptr;
+    ring_bytes = 0;
   }
   template <typename Tp>
   int upload(Tp** p, const Tp* h, size_t n) {
@@ -1058,6 +1154,22 @@ struct af_net {
 
 extern "C" int af_version(void) { return AF_ABI_VERSION; }
 extern "C" const char* af_last_error(void) { return g_err.c_str(); }
+
+extern "C" int af_release_cached_memory(void) {
+  BlockCache& c = cache();
+  std::lock_guard<std::mutex> lk(c.mu);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto& kv : c.dev) {
+    cudaSetDevice(kv.first.first);
+    cudaFree(kv.second);
+  }
+  cudaSetDevice(prev);
+  for (auto& kv : c.host) cudaFreeHost(kv.second);
+  c.dev.clear(); c.host.clear();
+  c.dev_bytes = c.host_bytes = 0;
+  return AF_OK;
+}
 
 extern "C" void af_desc_defaults(af_desc* d) {
   memset(d, 0, sizeof(*d));
@@ -1311,10 +1423,11 @@ extern "C" void af_net_destroy(af_net* n) {
   if (!n) return;
   cudaSetDevice(n->device);
   if (n->stream) cudaStreamSynchronize(n->stream);
-  for (void* p : n->allocs) cudaFree(p);
+  if (n->copy_stream) cudaStreamSynchronize(n->copy_stream);
+  for (auto& blk : n->allocs) af_net::release_block(n->device, blk.first, blk.second);
   for (cudaEvent_t ev : n->snap_event) cudaEventDestroy(ev);
   for (int k = 0; k < af_net::kRing; ++k) if (n->ring_done[k]) cudaEventDestroy(n->ring_done[k]);
-  if (n->ring) cudaFreeHost(n->ring);
+  n->ring_free();
   if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
   if (n->own_stream && n->stream) cudaStreamDestroy(n->stream);
   delete n;
@@ -1538,8 +1651,7 @@ extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t fir
   n->h_flow = n->h_area = n->h_press = n->h_outlet = nullptr;
   if (n->ring) {
     if (n->copy_stream) AF_CUDA(cudaStreamSynchronize(n->copy_stream));   // undelivered copies are dropped
-    cudaFreeHost(n->ring);
-    n->ring = nullptr;
+    n->ring_free();
   }
   for (int k = 0; k < af_net::kRing; ++k) n->ring_snap[k] = -1;
   return AF_OK;
@@ -1556,10 +1668,9 @@ extern "C" int af_net_set_store_host(af_net* n, double* flow, double* area, doub
   n->slot_doubles = snapshot_doubles(n);
   if (n->ring) {
     AF_CUDA(cudaStreamSynchronize(n->copy_stream));
-    cudaFreeHost(n->ring);
-    n->ring = nullptr;
+    n->ring_free();
   }
-  AF_CUDA(cudaHostAlloc((void**)&n->ring, n->slot_doubles * af_net::kRing * sizeof(double), cudaHostAllocDefault));
+  if ((rc = n->ring_alloc(n->slot_doubles * af_net::kRing * sizeof(double)))) return rc;
   for (int k = 0; k < af_net::kRing; ++k) {
     if (!n->ring_done[k]) AF_CUDA(cudaEventCreateWithFlags(&n->ring_done[k], cudaEventDisableTiming));
     n->ring_snap[k] = -1;

@@ -124,6 +124,13 @@ void af_desc_defaults(af_desc* d);
 int af_net_create(const af_desc* d, af_net** out);
 void af_net_destroy(af_net* net);
 
+/* Device and pinned-host blocks of destroyed / reconfigured handles are cached
+ * (exact-size reuse, AF_CACHE_MB caps the device bytes, default 4096, 0 disables)
+ * so that loops over ArteryNetwork(param).solve() (the reference's way to run a
+ * parameter study) do not pay cudaMalloc/cudaHostAlloc every time.  This call
+ * returns everything cached to the driver. */
+int af_release_cached_memory(void);
+
 /* Replaces the time loop body (an:908-946) for global steps
  * [n_first, n_first + n_steps): step g has n_cycle = g / Nt, n = g % Nt; it
  * applies set_bcs(q_ins[(n+1) % Nt]) (an:916), solves and updates every

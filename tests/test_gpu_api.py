@@ -415,6 +415,7 @@ def test_size_limits():
 
 def test_store_reconfiguration_does_not_accumulate_device_memory():
     import torch
+    import bloodflow_b200
     from bloodflow_b200 import _ffi
     net = _raw_network([[0, 1, 2]], [1, 2], Nx=1023)
     mask = np.ones(8, dtype=np.uint8)
@@ -425,9 +426,40 @@ def test_store_reconfiguration_does_not_accumulate_device_memory():
     free0 = torch.cuda.mem_get_info(0)[0]
     for cap in (4097, 4098, 4099, 4100):
         net.set_store(mask, 0, cap, fields)
+    bloodflow_b200.release_cached_memory()                # released blocks sit in the library's cache
     free1 = torch.cuda.mem_get_info(0)[0]
     assert free0 - free1 < 64 << 20                       # the old buffers were released, not kept
     net.step(3, 2)
     again = net.fetch_snapshots()
     assert list(first['step']) == [0, 1, 2] and list(again['step']) == [3, 4]
     net.close()
+
+
+def test_recycled_blocks_do_not_leak_state_between_networks():
+    """Blocks of a destroyed handle are reused by the next same-shaped one
+    (af_release_cached_memory): a network built on recycled memory must give
+    bitwise the results of one built on fresh memory."""
+    import bloodflow_b200
+
+    def run(scale):
+        net = _raw_network([[0, 1, 2]], [1, 2], Nx=200)
+        if scale != 1.0:
+            A, q = net.get_state()
+            net.set_state(A * scale, q * scale)
+        net.set_store(np.ones(8, dtype=np.uint8), 0, 16, 1 | 2 | 4 | 8)
+        net.step(0, 12)
+        out = (net.get_state(), net.get_bc(), net.get_dex(), net.get_junction_x(), net.fetch_snapshots())
+        net.close()
+        return out
+
+    bloodflow_b200.release_cached_memory()
+    fresh = run(1.0)
+    run(1.3)                                   # leaves different data in the cached blocks
+    recycled = run(1.0)
+    for a, b in zip(fresh[0], recycled[0]):
+        np.testing.assert_array_equal(a, b)
+    for k in (1, 2, 3):
+        np.testing.assert_array_equal(fresh[k], recycled[k])
+    for key in ('flow', 'area', 'pressure', 'outlet_pressure'):
+        np.testing.assert_array_equal(fresh[4][key], recycled[4][key])
+    bloodflow_b200.release_cached_memory()
