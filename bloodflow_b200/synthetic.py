@@ -40,8 +40,14 @@ def tree_param(order, Nx, Nt, N_cycles=1, Nt_store=None, N_cycles_store=1, Ru0=0
     mult = np.ones(N)
     mult[0] = Ru0
     param = dict(PHYS)
+    # "untapered leaves: R_term = leaf Ru"  has to hold bitwise, or the leaves count as
+    # (1e-16-)tapered vessels and take the pow/exp + coefficient-table path: generate R_term by the
+    # same repeated product build_geometry uses for the leaf radii (an:195-217)
+    r_leaf = Ru0
+    for _ in range(order - 1):
+        r_leaf = alpha * r_leaf * 1.0
     param.update(order=order, Ru=mult.copy(), Rd=mult.copy(), alpha=alpha, L=L,
-                 R_term=Ru0 * alpha ** (order - 1), p_term=6000.0,
+                 R_term=r_leaf, p_term=6000.0,
                  R1=np.full(n_leaves, R1), R2=np.full(n_leaves, R2), CT=np.full(n_leaves, CT))
     geo = dict(Nx=Nx, Nt=Nt, N_cycles=N_cycles)
     sol = dict(inlet_flow_location=inlet, output_location=output_location, theta=theta,
