@@ -82,6 +82,7 @@ PROTOTYPES = {
     'af_eval_flux_source': (c_int, [Handle, c_i32, c_i32, c_i32, P_dbl, P_dbl, P_dbl]),
     'af_eval_u_half': (c_int, [Handle, c_i32, c_i32, c_dbl, c_dbl, P_dbl, P_dbl, P_dbl]),
     'af_eval_cfl_term': (c_int, [Handle, c_i32, c_i32, c_dbl, c_dbl, c_dbl, P_dbl]),
+    'af_eval_math': (c_int, [c_i32, c_i32, c_i32, P_dbl, P_dbl]),
     'af_junction_cfl_dex': (c_int, [Handle, c_i32, c_i32, P_dbl]),
     'af_junction_eval': (c_int, [Handle, c_i32, c_i32, P_dbl, P_dbl, P_dbl, P_dbl]),
     'af_junction_newton': (c_int, [Handle, c_i32, c_i32, P_dbl, P_dbl, c_i32, c_dbl, P_i32]),

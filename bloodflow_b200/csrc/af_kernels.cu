@@ -884,6 +884,12 @@ __global__ void k_unpack(NetDev nd, int cur, const double* A, const double* q) {
 // ---------------------------------------------------------------------------
 // mode 0: flux/source at points x with states U -> out[n][3]; 1: u_half (x = x0, x1; U = U0, U1) -> out[2];
 // 2: CFL_term at x[0] with U[0..1] -> out[0]
+// af_eval_math: the kernel-side elementary functions, for their accuracy test
+__global__ void k_eval_math(int which, int n, const double* x, double* out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = which == 0 ? af_rcp_fast(x[i]) : af_rsqrt_fast(x[i]);
+}
+
 __global__ void k_eval_bc(NetDev nd, int ba, int mode, int n, const double* x, const double* U, double* out) {
   const Vessel v = nd.ves[ba];
   if (mode == 0) {
@@ -1938,6 +1944,22 @@ extern "C" int af_eval_cfl_term(af_net* n, int32_t network, int32_t artery, doub
   k_eval_bc<<<1, 32, 0, n->stream>>>(n->nd, network * n->nd.na + artery, 2, 1, s, s + 1, s + 1024);
   AF_CUDA(cudaGetLastError());
   return d2h(n, M, s + 1024, 1);
+}
+
+extern "C" int af_eval_math(int32_t device, int32_t which, int32_t cnt, const double* x, double* out) {
+  if (!x || !out || cnt < 0 || which < 0 || which > 1) return fail(AF_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(AF_ENODEVICE, "no CUDA device");
+  AF_CUDA(cudaSetDevice(device));
+  if (cnt == 0) return AF_OK;
+  double* d = nullptr;
+  AF_CUDA(cudaMalloc(&d, 2 * (size_t)cnt * sizeof(double)));
+  cudaMemcpy(d, x, cnt * sizeof(double), cudaMemcpyHostToDevice);
+  k_eval_math<<<148, 256>>>(which, cnt, d, d + cnt);
+  cudaError_t e = cudaMemcpy(out, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(AF_ECUDA, cudaGetErrorString(e));
+  return AF_OK;
 }
 
 static int junction_call(af_net* n, int network, int junction, int mode, const double* dex3, const double* x,

@@ -26,33 +26,32 @@ namespace af {
 #define af_rsqrt(x) (1.0 / sqrt(x))
 #endif
 
-// Branch-free reciprocal and reciprocal square root for the artery kernel: the
-// hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-23) refined to ~1 ulp in straight-line
-// FMAs.  The library versions guard every call with a slow-path branch for denormal /
-// huge arguments, which cuts the assembly of a cell into a dozen small basic blocks;
-// areas and 2x2 block determinants are O(1) numbers, and 0 / negative / non-finite
-// arguments still come out as inf / NaN and are caught by the Newton loop's
-// non-finite test.  Host builds (tests/host_harness) use the plain expressions.
+// Branch-free reciprocal and reciprocal square root: the hardware seed
+// (MUFU.RCP64H / MUFU.RSQ64H, relative error ~2^-23) refined by ONE cubically
+// convergent step in straight-line FMAs (error after the step ~2^-69, i.e. the
+// result is the rounding of the last FMA: < 1 ulp, checked against 1/x and
+// 1/sqrt(x) by tests/test_gpu_api.py through af_eval_math).  The library versions
+// guard every call with a slow-path branch for denormal / huge arguments, which cuts
+// the assembly of a cell into a dozen small basic blocks and lengthens the serial
+// chain of the Windkessel iteration; areas and 2x2 block determinants are O(1)
+// numbers, and 0 / negative / non-finite arguments still come out as inf / NaN and
+// are caught by the non-finite tests.  Host builds (tests/host_harness) use the plain
+// expressions.
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ double af_rcp_fast(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  e = fma(e, e, e);             // e + e^2: one cubic step, 2^-23 -> 2^-69
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);          // clean-up step to ~1 ulp
-  return fma(y, e, y);
+  double e = fma(-x, y, 1.0);   // 1 - x y
+  e = fma(e, e, e);             // e + e^2
+  return fma(y, e, y);          // y (1 + e + e^2) = 1/x (1 - e^3)
 }
 __device__ __forceinline__ double af_rsqrt_fast(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double t = x * y;
   double e = fma(-t, y, 1.0);                   // 1 - x y^2
-  double p = fma(0.375, e, 0.5) * e;            // e/2 + 3 e^2/8: cubic step, 2^-23 -> 2^-67
-  y = fma(y, p, y);
-  t = x * y;
-  e = fma(-t, y, 1.0);
-  return fma(0.5 * y, e, y);                    // clean-up step to ~1 ulp
+  double p = fma(0.375, e, 0.5) * e;            // e/2 + 3 e^2/8
+  return fma(y, p, y);                          // y (1 - e)^-1/2 up to (5/16) e^3
 }
 #else
 inline double af_rcp_fast(double x) { return 1.0 / x; }
@@ -202,7 +201,7 @@ AF_HD WkResult windkessel_picard(const Vessel& v, double dt, double dex, double 
     p3 = p2; p2 = p1; p1 = p;
     Am2 = Am1; Am1 = Am0;
     Am0 = K2 - K3 * p1;
-    p = K4 - K5 * af_rsqrt(Am0);
+    p = K4 - K5 * af_rsqrt_fast(Am0);
     ++k;
     if (fabs(p - p1) < tol) break;
     // The map is deterministic: once an iterate repeats (round-off limit

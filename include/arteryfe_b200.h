@@ -224,6 +224,10 @@ int af_eval_u_half(af_net* net, int32_t network, int32_t artery, double x0, doub
                    const double U1[2], double out[2]);
 /* CFL_term (ar:304-325) at point x with state (A, q) */
 int af_eval_cfl_term(af_net* net, int32_t network, int32_t artery, double x, double A, double q, double* M);
+/* The kernels' branch-free reciprocal (which = 0) and reciprocal square root
+ * (which = 1) at n points: validation of their accuracy against 1/x, 1/sqrt(x)
+ * (the reference uses the IEEE operations of numpy / the form compiler). */
+int af_eval_math(int32_t device, int32_t which, int32_t n, const double* x, double* out);
 /* adjust_bifurcation_step (an:713-737): the common dex of one junction */
 int af_junction_cfl_dex(af_net* net, int32_t network, int32_t junction, double* dex);
 /* problem_function / jacobian (an:476-665) at x[18] with the given dex of
