@@ -22,6 +22,7 @@ import numpy as np
 
 from . import _ffi
 from .engine import DeviceNetwork
+from .synthetic import leaf_radius
 
 SEED = 20260000
 
@@ -44,9 +45,13 @@ def perturb_param(param, i, seed=SEED):
     p.param['k3'] = p.param['k3'] * s
     p.param['Ru'] = np.array(p.param['Ru'], dtype=float)
     p.param['Rd'] = np.array(p.param['Rd'], dtype=float)
+    nominal_leaf = leaf_radius(p.param['Ru'][0], p.param['alpha'], p.param['order']) if 'alpha' in p.param else None
+    untapered_leaves = nominal_leaf is not None and p.param['R_term'] == nominal_leaf
     p.param['Ru'][0] *= r
     p.param['Rd'][0] *= r
-    p.param['R_term'] = p.param['R_term'] * r
+    # leaves that are untapered in the nominal tree (R_term == leaf Ru bitwise) stay so
+    p.param['R_term'] = (leaf_radius(p.param['Ru'][0], p.param['alpha'], p.param['order']) if untapered_leaves
+                         else p.param['R_term'] * r)
     p.param['R1'] = np.atleast_1d(p.param['R1']) * f1
     p.param['R2'] = np.atleast_1d(p.param['R2']) * f2
     p.param['CT'] = np.atleast_1d(p.param['CT']) * fc

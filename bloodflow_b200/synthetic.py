@@ -31,6 +31,15 @@ def leaf_windkessel(order, Ru0=0.37, alpha=0.8, mean_flow=5.5, tau=0.0186, phys=
     return R1_eff / 0.3, R2_eff / 0.01, tau / R2_eff
 
 
+def leaf_radius(Ru0, alpha, order):
+    """Upstream radius of a last-generation vessel exactly as build_geometry
+    (an:195-217) produces it: the repeated product alpha*Ru_parent*1.0."""
+    r = float(Ru0)
+    for _ in range(order - 1):
+        r = alpha * r * 1.0
+    return r
+
+
 def tree_param(order, Nx, Nt, N_cycles=1, Nt_store=None, N_cycles_store=1, Ru0=0.37, alpha=0.8, L=20.0,
                theta=0.55, output_location='output/synthetic', inlet=INLET, store_area=1, store_pressure=1):
     """ParamParser-like description of a symmetric tree of ``order`` levels."""
@@ -43,9 +52,7 @@ def tree_param(order, Nx, Nt, N_cycles=1, Nt_store=None, N_cycles_store=1, Ru0=0
     # "untapered leaves: R_term = leaf Ru"  has to hold bitwise, or the leaves count as
     # (1e-16-)tapered vessels and take the pow/exp + coefficient-table path: generate R_term by the
     # same repeated product build_geometry uses for the leaf radii (an:195-217)
-    r_leaf = Ru0
-    for _ in range(order - 1):
-        r_leaf = alpha * r_leaf * 1.0
+    r_leaf = leaf_radius(Ru0, alpha, order)
     param.update(order=order, Ru=mult.copy(), Rd=mult.copy(), alpha=alpha, L=L,
                  R_term=r_leaf, p_term=6000.0,
                  R1=np.full(n_leaves, R1), R2=np.full(n_leaves, R2), CT=np.full(n_leaves, CT))
