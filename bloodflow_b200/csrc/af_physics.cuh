@@ -448,10 +448,10 @@ AF_HD int solve3(double M[9], double b[3]) {
 // Returns 1 if a pivot vanishes.
 AF_HD int solve_arrow3(double d0, double d1, double d2, double m1, double e1, double m2, double e2, double b[3]) {
   if (e1 == 0.0 || e2 == 0.0) return 1;
-  const double i1 = 1.0 / e1, i2 = 1.0 / e2;
+  const double i1 = af_rcp_fast(e1), i2 = af_rcp_fast(e2);
   const double den = d0 - d1 * (m1 * i1) - d2 * (m2 * i2);
   if (den == 0.0) return 1;
-  const double x0 = (b[0] - d1 * (b[1] * i1) - d2 * (b[2] * i2)) / den;
+  const double x0 = (b[0] - d1 * (b[1] * i1) - d2 * (b[2] * i2)) * af_rcp_fast(den);
   b[1] = (b[1] - m1 * x0) * i1;
   b[2] = (b[2] - m2 * x0) * i2;
   b[0] = x0;
@@ -642,14 +642,14 @@ AF_HD void jvessel_prepare(JVessel& j, int v, const Vessel& ves, const double* A
 // xv = the six unknowns of this vessel: q^{n+1}, q^{n+1/2}, q ghost, A^{n+1}, A^{n+1/2}, A ghost
 AF_HD void jvessel_linearise(const JVessel& j, const double xv[6], JVesselLin& o) {
   const double q1 = xv[0], qh = xv[1], qg = xv[2], A1 = xv[3], Ah = xv[4], Ag = xv[5];
-  const double y = af_rsqrt(Ag), sA = Ag * y, iA = y * y;
+  const double y = af_rsqrt_fast(Ag), sA = Ag * y, iA = y * y;
   const double Fg2 = qg * qg + j.gF * sA;
   const double Sg2 = j.src_k * qg * y + j.gS1 * sA - j.gS2 * Ag;
   o.y0 = 2.0 * qh - j.qh - qg;
   o.y3 = 2.0 * Ah - j.Ah - Ag;
   o.y12 = q1 - j.qe + j.s * j.dtdex * (Fg2 - j.Fh2) - j.hdt * (Sg2 + j.Sh2);
   o.y15 = A1 - j.Ae + j.s * j.dtdex * (qg - j.qh);
-  const double yh = af_rsqrt(Ah), y1 = af_rsqrt(A1);
+  const double yh = af_rsqrt_fast(Ah), y1 = af_rsqrt_fast(A1);
   o.ph = j.fe * (1.0 - j.sA0e * yh);
   o.pf = j.fe * (1.0 - j.sA0e * y1);
   o.dPh = j.kP * (yh * yh * yh);
