@@ -194,7 +194,7 @@ __device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, 
     double m = junction_cfl(nd.ves[ba], v, A + off, q + off, nd.Nx);
     M = m < M ? m : M;
   }
-  double dex = (1.0 + nd.cfl_margin) * nd.dt / M;
+  double dex = AF_DIV((1.0 + nd.cfl_margin) * nd.dt, M);
   JVessel jv[3];
   for (int v = 0; v < 3; ++v) {
     int ba = b * nd.na + ia[v];
@@ -237,7 +237,7 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
     M = 1.0e300;
     M = m0 < M ? m0 : M; M = m1 < M ? m1 : M; M = m2 < M ? m2 : M;
   }
-  dex = (1.0 + nd.cfl_margin) * nd.dt / M;
+  dex = AF_DIV((1.0 + nd.cfl_margin) * nd.dt, M);
   JVessel jv;
   jvessel_prepare(jv, v, ves, A, q, nd.Nx, nd.dt, dex);
   const double dtdex_p = __shfl_sync(FULL, jv.dtdex, 0), dtdex_d1 = __shfl_sync(FULL, jv.dtdex, 1);

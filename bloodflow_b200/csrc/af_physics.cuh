@@ -57,6 +57,16 @@ __device__ __forceinline__ double af_rsqrt_fast(double x) {
 inline double af_rcp_fast(double x) { return 1.0 / x; }
 inline double af_rsqrt_fast(double x) { return 1.0 / sqrt(x); }
 #endif
+// a / b and sqrt(x > 0) of the boundary-condition code (the serial chain of the lone
+// warp that owns a junction): through the branch-free functions on the device (<= 2 ulp),
+// the IEEE operations on the host.
+#ifdef __CUDA_ARCH__
+#define AF_DIV(a, b) ((a) * af_rcp_fast(b))
+__device__ __forceinline__ double af_sqrt_pos(double x) { return x * af_rsqrt_fast(x); }
+#else
+#define AF_DIV(a, b) ((a) / (b))
+inline double af_sqrt_pos(double x) { return sqrt(x); }
+#endif
 
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSqrtPi = 1.7724538509055159;   // == (double)sqrt((double)pi)
@@ -125,9 +135,10 @@ AF_HD Coef coef_at(const Vessel& v, double x) {
 // P1 point evaluation of (A, q) on the uniform mesh x_j = j*dx  ([3P] a15)
 AF_HD void interp_state(const double* A, const double* q, int Nx, double dx, double x,
                         double& Ax, double& qx) {
-  int j = (int)floor(x / dx);
+  const double inv_dx = af_rcp_fast(dx);
+  int j = (int)floor(x * inv_dx);
   j = j < 0 ? 0 : (j > Nx - 1 ? Nx - 1 : j);
-  double xi = (x - j * dx) / dx;
+  double xi = (x - j * dx) * inv_dx;
   Ax = A[j] * (1.0 - xi) + A[j + 1] * xi;
   qx = q[j] * (1.0 - xi) + q[j + 1] * xi;
 }
@@ -136,12 +147,12 @@ AF_HD void interp_state(const double* A, const double* q, int Nx, double dx, dou
 // boundary-condition physics  (an:282-358)
 // ---------------------------------------------------------------------------
 // flux: F = (q, q^2 + f*sqrt(A0*A))   -- no "/A" (an:300)
-AF_HD double bc_flux2(const Coef& c, double A, double q) { return q * q + c.f * sqrt(c.A0 * A); }
+AF_HD double bc_flux2(const Coef& c, double A, double q) { return q * q + c.f * af_sqrt_pos(c.A0 * A); }
 
 // source: S2 (an:322-325)
 AF_HD double bc_source2(const Vessel& v, const Coef& c, double A, double q) {
-  double sA = sqrt(A);
-  return v.src_k * q / sA + (2.0 * sA * (kSqrtPi * c.f + sqrt(c.A0) * c.dfdr) - A * c.dfdr) * c.drdx;
+  double isA = af_rsqrt_fast(A), sA = A * isA;
+  return v.src_k * q * isA + (2.0 * sA * (kSqrtPi * c.f + af_sqrt_pos(c.A0) * c.dfdr) - A * c.dfdr) * c.drdx;
 }
 
 // compute_U_half (an:329-358): note dt/(x1-x0) and dt/4
@@ -150,17 +161,18 @@ AF_HD void u_half(const Vessel& v, double dt, double x0, double x1, double A0s, 
   Coef c0 = coef_at(v, x0), c1 = coef_at(v, x1);
   double F0 = bc_flux2(c0, A0s, q0s), F1 = bc_flux2(c1, A1s, q1s);
   double S0 = bc_source2(v, c0, A0s, q0s), S1 = bc_source2(v, c1, A1s, q1s);
-  double r = dt / (x1 - x0);
+  double r = AF_DIV(dt, x1 - x0);
   Ah = (A0s + A1s) / 2.0 - r * (q1s - q0s);
   qh = (q0s + q1s) / 2.0 - r * (F1 - F0) + dt / 4.0 * (S0 + S1);
 }
 
 // CFL_term (ar:304-325)
 AF_HD double cfl_term(const Vessel& v, const Coef& c, double A, double q) {
-  double w = sqrt(c.f / 2.0 / v.rho * sqrt(c.A0 / A));
-  double u = q / A;
+  const double iA = af_rcp_fast(A);
+  double w = af_sqrt_pos(AF_DIV(c.f / 2.0, v.rho) * af_sqrt_pos(c.A0 * iA));
+  double u = q * iA;
   double a = fabs(u + w), b = fabs(u - w);
-  return 1.0 / (a > b ? a : b);
+  return af_rcp_fast(a > b ? a : b);
 }
 
 AF_HD double outlet_pressure(const Vessel& v, double A) {   // ar:285-301
@@ -622,11 +634,11 @@ AF_HD void jvessel_prepare(JVessel& j, int v, const Vessel& ves, const double* A
     u_half(ves, dt, xe, xi, Ae, qe, Ai, qi, Ah, qh);
   const Coef ch = coef_at(ves, xh), cg = coef_at(ves, xg), cj = coef_at(ves, xj);
   j.s = v == 0 ? 1.0 : -1.0;
-  j.dt = dt; j.dtdex = dt / dex; j.hdt = dt / 2.0;
+  j.dt = dt; j.dtdex = AF_DIV(dt, dex); j.hdt = dt / 2.0;
   j.qe = qe; j.Ae = Ae; j.qh = qh; j.Ah = Ah;
   j.Fh2 = bc_flux2(ch, Ah, qh);
   j.Sh2 = bc_source2(ves, ch, Ah, qh);
-  const double sg = sqrt(cg.A0), sj = sqrt(cj.A0);
+  const double sg = af_sqrt_pos(cg.A0), sj = af_sqrt_pos(cj.A0);
   j.gF = cg.f * sg;
   j.gS1 = 2.0 * (kSqrtPi * cg.f + sg * cg.dfdr) * cg.drdx;
   j.gS2 = cg.dfdr * cg.drdx;
@@ -635,7 +647,7 @@ AF_HD void jvessel_prepare(JVessel& j, int v, const Vessel& ves, const double* A
   j.jS2 = cj.dfdr * cj.drdx;
   j.src_k = ves.src_k; j.rk = ves.rpi_dbRe;
   j.fe = v == 0 ? ves.fL : ves.f0;
-  j.sA0e = sqrt(v == 0 ? ves.A0L : ves.A00);
+  j.sA0e = af_sqrt_pos(v == 0 ? ves.A0L : ves.A00);
   j.kP = j.fe * j.sA0e / 2.0;
 }
 
