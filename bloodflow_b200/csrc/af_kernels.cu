@@ -263,7 +263,7 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
     double nrm = 0.0;
 #pragma unroll
     for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
-    if (sqrt(nrm) < nd.junction_tol) break;
+    if (nrm < nd.junction_tol * nd.junction_tol) break;      // ||y|| < tol (an:684), no sqrt on the chain
     if (junction_update(l, dtdex_p, dtdex_d1, y)) { singular = true; break; }
 #pragma unroll
     for (int i = 0; i < 18; ++i) x[i] -= y[i];
@@ -743,10 +743,11 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
     }
     cta_sync<T>();
     double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
-    double r = sqrt(block_sum<T>(part, red));     // its two barriers also publish pa/pc
-    // ---- [3P] NewtonSolver::converged ---------------------------------------
+    const double r2 = block_sum<T>(part, red);    // its two barriers also publish pa/pc
+    const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
+    // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ------------------
     if (first) r_first = r;
-    if (r / r_first < nd.newton_rtol || r < nd.newton_atol) break;
+    if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
     if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
     if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
     // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------

@@ -713,7 +713,7 @@ AF_HD int junction_newton_fast(const JVessel jv[3], double* x, int k_max, double
     double nrm = 0.0;
 #pragma unroll
     for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
-    if (sqrt(nrm) < tol) break;
+    if (nrm < tol * tol) break;          // ||y|| < tol (an:684) without the square root on the serial chain
     if (junction_update(l, jv[0].dtdex, jv[1].dtdex, y)) return -1;
 #pragma unroll
     for (int i = 0; i < 18; ++i) x[i] -= y[i];
