@@ -20,12 +20,6 @@
 
 namespace af {
 
-#ifdef __CUDA_ARCH__
-#define af_rsqrt(x) rsqrt(x)
-#else
-#define af_rsqrt(x) (1.0 / sqrt(x))
-#endif
-
 // Branch-free reciprocal and reciprocal square root: the hardware seed
 // (MUFU.RCP64H / MUFU.RSQ64H, relative error ~2^-23) refined by ONE cubically
 // convergent step in straight-line FMAs (error after the step ~2^-69, i.e. the
