@@ -110,6 +110,17 @@ def measured_traffic(kernel):
         return None
 
 
+def measured_pipe(kernel):
+    """FP64-pipe and issue-slot utilisation of the dominant kernel from the same committed capture."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    try:
+        with open(path) as fh:
+            t = json.load(fh)[kernel]
+        return {"fp64_pipe_active_pct": t["fp64_pipe_active_pct"], "issue_active_pct": t["issue_active_pct"]}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -316,7 +327,8 @@ def main():
                         "the kernel is latency/FP64-bound, not HBM-bound (DESIGN.md)",
                 "fp64": {"achieved_tflops": flops_per_node_step * nodes / (art_us * 1e-6) / 1e12,
                          "peak_tflops": fp64_peak, "flops_per_vertex_step": flops_per_node_step,
-                         "newton_its_per_artery_step": its_per_step},
+                         "newton_its_per_artery_step": its_per_step,
+                         "ncu": measured_pipe("k_artery<256>") if (args.order, args.Nx) == (ORDER, NX) else None},
             },
             "phases_us": phase,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e['h2d'] / K,
