@@ -477,3 +477,28 @@ def test_branch_free_reciprocals_are_accurate_to_an_ulp(which, ref):
     err = np.abs(out / ref(x) - 1.0)
     assert err.max() < 2.3e-16, err.max()
     assert np.mean(out == ref(x)) > 0.5            # most results are the correctly rounded value
+
+
+def test_cache_can_be_disabled(tmp_path):
+    """AF_CACHE_MB=0: released blocks go straight back to the driver (checked in a
+    fresh process, the cap is read once per process)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "from bloodflow_b200.engine import DeviceNetwork\n"
+        "o = np.ones(3)\n"
+        "net = DeviceNetwork(1023, 8, 1.0, 1e-3, [[0, 1, 2]], [1, 2], k1=2e7, k2=-22.5, k3=8.65e5, rho=1.0, Re=100.0,\n"
+        "                    db=1.0, p0=1.0, Ru=0.4 * o, Rd=0.4 * o, L=5 * o, q0=o, R1=np.ones(2), R2=np.ones(2),\n"
+        "                    CT=np.ones(2), q_ins=np.ones(8))\n"
+        "net.set_store(np.ones(8, dtype=np.uint8), 0, 2048, 7)\n"
+        "net.step(0, 4); net.sync()\n"
+        "used = torch.cuda.mem_get_info(0)[0]\n"
+        "net.close()\n"
+        "freed = torch.cuda.mem_get_info(0)[0] - used\n"
+        "assert freed > 100 << 20, freed\n"
+        "print('freed', freed >> 20, 'MB')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, AF_CACHE_MB='0')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
