@@ -1024,31 +1024,49 @@ AF_HD Elim make_elim(const Row& w) {
   return e;
 }
 
+// w.dg -= a * b (2x2 blocks) and w.r -= a * g, as FMA chains: two instructions per
+// entry instead of multiply, multiply-add and subtract
+AF_HD void sub_mul2(double d[4], const double a[4], const double b[4]) {
+  d[0] = fma(-a[1], b[2], fma(-a[0], b[0], d[0]));
+  d[1] = fma(-a[1], b[3], fma(-a[0], b[1], d[1]));
+  d[2] = fma(-a[3], b[2], fma(-a[2], b[0], d[2]));
+  d[3] = fma(-a[3], b[3], fma(-a[2], b[1], d[3]));
+}
+
+AF_HD void sub_mulv(double r[2], const double a[4], const double g[2]) {
+  r[0] = fma(-a[1], g[1], fma(-a[0], g[0], r[0]));
+  r[1] = fma(-a[3], g[1], fma(-a[2], g[0], r[1]));
+}
+
+// o = -(a * b)
+AF_HD void neg_mul2(const double a[4], const double b[4], double o[4]) {
+  o[0] = fma(-a[1], b[2], -a[0] * b[0]);
+  o[1] = fma(-a[1], b[3], -a[0] * b[1]);
+  o[2] = fma(-a[3], b[2], -a[2] * b[0]);
+  o[3] = fma(-a[3], b[3], -a[2] * b[1]);
+}
+
 // eliminate the LEFT neighbour of row w (coupled through w.lo)
 AF_HD void apply_left(Row& w, const Elim& e) {
+  sub_mul2(w.dg, w.lo, e.Q);
+  sub_mulv(w.r, w.lo, e.g);
   double m[4];
-  mul2(w.lo, e.Q, m);
-  w.dg[0] -= m[0]; w.dg[1] -= m[1]; w.dg[2] -= m[2]; w.dg[3] -= m[3];
-  w.r[0] -= w.lo[0] * e.g[0] + w.lo[1] * e.g[1];
-  w.r[1] -= w.lo[2] * e.g[0] + w.lo[3] * e.g[1];
-  mul2(w.lo, e.P, m);
-  w.lo[0] = -m[0]; w.lo[1] = -m[1]; w.lo[2] = -m[2]; w.lo[3] = -m[3];
+  neg_mul2(w.lo, e.P, m);
+  w.lo[0] = m[0]; w.lo[1] = m[1]; w.lo[2] = m[2]; w.lo[3] = m[3];
 }
 
 // eliminate the RIGHT neighbour of row w (coupled through w.up)
 AF_HD void apply_right(Row& w, const Elim& e) {
+  sub_mul2(w.dg, w.up, e.P);
+  sub_mulv(w.r, w.up, e.g);
   double m[4];
-  mul2(w.up, e.P, m);
-  w.dg[0] -= m[0]; w.dg[1] -= m[1]; w.dg[2] -= m[2]; w.dg[3] -= m[3];
-  w.r[0] -= w.up[0] * e.g[0] + w.up[1] * e.g[1];
-  w.r[1] -= w.up[2] * e.g[0] + w.up[3] * e.g[1];
-  mul2(w.up, e.Q, m);
-  w.up[0] = -m[0]; w.up[1] = -m[1]; w.up[2] = -m[2]; w.up[3] = -m[3];
+  neg_mul2(w.up, e.Q, m);
+  w.up[0] = m[0]; w.up[1] = m[1]; w.up[2] = m[2]; w.up[3] = m[3];
 }
 
 AF_HD void back_sub(const Elim& e, const double xl[2], const double xr[2], double x[2]) {
-  x[0] = e.g[0] - (e.P[0] * xl[0] + e.P[1] * xl[1]) - (e.Q[0] * xr[0] + e.Q[1] * xr[1]);
-  x[1] = e.g[1] - (e.P[2] * xl[0] + e.P[3] * xl[1]) - (e.Q[2] * xr[0] + e.Q[3] * xr[1]);
+  x[0] = fma(-e.Q[1], xr[1], fma(-e.Q[0], xr[0], fma(-e.P[1], xl[1], fma(-e.P[0], xl[0], e.g[0]))));
+  x[1] = fma(-e.Q[3], xr[1], fma(-e.Q[2], xr[0], fma(-e.P[3], xl[1], fma(-e.P[2], xl[0], e.g[1]))));
 }
 
 }  // namespace af
