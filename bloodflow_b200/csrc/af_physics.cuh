@@ -780,16 +780,15 @@ struct PointTerms {
 template <bool JAC>
 AF_HD PointTerms point_terms(double A, double q, double c1, double t2, double t3, double Kr) {
   PointTerms t;
-  double isA = af_rsqrt_fast(A);
-  double sA = A * isA;
-  double inv = isA * isA;
-  double qi = q * inv;
-  t.F2 = q * qi + c1 * sA;
-  t.S2 = -Kr * q * isA + 2.0 * sA * t2 - A * t3;
+  const double isA = af_rsqrt_fast(A);
+  const double sA = A * isA;
+  const double qi = q * (isA * isA);
+  t.F2 = fma(q, qi, c1 * sA);
+  t.S2 = fma(-Kr * q, isA, fma(2.0 * t2, sA, -A * t3));
   if (JAC) {
-    t.dF2dA = -qi * qi + 0.5 * c1 * isA;
+    t.dF2dA = fma(-qi, qi, (0.5 * c1) * isA);
     t.dF2dq = 2.0 * qi;
-    t.dS2dA = 0.5 * Kr * qi * isA + t2 * isA - t3;
+    t.dS2dA = fma(isA, fma(0.5 * Kr, qi, t2), -t3);
     t.dS2dq = -Kr * isA;
   }
   return t;
@@ -808,6 +807,8 @@ struct CellInt {
 
 template <bool JAC>
 AF_HD CellInt cell_integrals(double h, double Kr, const CellCoef& cc, double Al, double Ar, double ql, double qr) {
+  // quadrature weight times the P1 shape-function products, folded at compile time so
+  // that every Gauss point adds one FMA to each of the 13 sums
   const double xi[3] = {kXi0, kXi1, kXi2};
   const double wq[3] = {kW0, kW1, kW2};
   CellInt o;
@@ -816,18 +817,18 @@ AF_HD CellInt cell_integrals(double h, double Kr, const CellCoef& cc, double Al,
   double c0 = 0.0, c1 = 0.0, d00 = 0.0, d01 = 0.0, d11 = 0.0;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    double p0 = 1.0 - xi[g], p1 = xi[g], w = wq[g];
+    const double p0 = 1.0 - xi[g], p1 = xi[g], w = wq[g];
+    const double k0 = w * p0, k1 = w * p1, k00 = w * p0 * p0, k01 = w * p0 * p1, k11 = w * p1 * p1;
     double A = Al * p0 + Ar * p1 + kDolfinEps, q = ql * p0 + qr * p1;
     PointTerms t = point_terms<JAC>(A, q, cc.c1[g], cc.t2[g], cc.t3[g], Kr);
-    sF += w * t.F2;
-    sS0 += w * p0 * t.S2;
-    sS1 += w * p1 * t.S2;
+    sF = fma(w, t.F2, sF);
+    sS0 = fma(k0, t.S2, sS0);
+    sS1 = fma(k1, t.S2, sS1);
     if (JAC) {
-      double wa = w * t.dF2dA, wb = w * t.dS2dA, wc = w * t.dF2dq, wd = w * t.dS2dq;
-      a0 += wa * p0; a1 += wa * p1;
-      b00 += wb * p0 * p0; b01 += wb * p0 * p1; b11 += wb * p1 * p1;
-      c0 += wc * p0; c1 += wc * p1;
-      d00 += wd * p0 * p0; d01 += wd * p0 * p1; d11 += wd * p1 * p1;
+      a0 = fma(k0, t.dF2dA, a0); a1 = fma(k1, t.dF2dA, a1);
+      b00 = fma(k00, t.dS2dA, b00); b01 = fma(k01, t.dS2dA, b01); b11 = fma(k11, t.dS2dA, b11);
+      c0 = fma(k0, t.dF2dq, c0); c1 = fma(k1, t.dF2dq, c1);
+      d00 = fma(k00, t.dS2dq, d00); d01 = fma(k01, t.dS2dq, d01); d11 = fma(k11, t.dS2dq, d11);
     }
   }
   // phi_l' = -1/h, phi_r' = +1/h; cell measure h
