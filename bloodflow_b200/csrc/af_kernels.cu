@@ -362,9 +362,10 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
 // (ensembles).  Two instantiations keep each kernel's code -- and the instruction
 // cache footprint of the lone warp that runs a task -- small.
 template <bool WARP>
-__global__ void k_boundary(NetDev nd, int cur, int log_slot) {
+__global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl) {
+  // networks b0 .. b0+nbl-1 (the whole batch, or the share of one sub-stream)
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long n_j = (long long)nd.nb * nd.nj, n_l = (long long)nd.nb * nd.nl;
+  long long n_j = (long long)nbl * nd.nj, n_l = (long long)nbl * nd.nl;
   if (WARP) {
     // Topology and vessel constants do not depend on the state: fetch them first,
     // they arrive while this kernel -- which may have been made resident under
@@ -375,12 +376,12 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
     int b = 0, j = 0, l = 0, ba = 0, ia[3] = {0, 0, 0};
     const bool is_junction = task < n_j, is_leaf = !is_junction && task < n_j + n_l;
     if (is_junction) {
-      b = (int)(task / nd.nj); j = (int)(task % nd.nj);
+      b = b0 + (int)(task / nd.nj); j = (int)(task % nd.nj);
       ia[0] = nd.j_p[j]; ia[1] = nd.j_d1[j]; ia[2] = nd.j_d2[j];
       ba = b * nd.na + ia[v];
     } else if (is_leaf) {
       task -= n_j;
-      b = (int)(task / nd.nl); l = (int)(task % nd.nl);
+      b = b0 + (int)(task / nd.nl); l = (int)(task % nd.nl);
       ba = b * nd.na + nd.leaf_art[l];
     }
     const Vessel ves = nd.ves[ba];
@@ -397,10 +398,10 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot) {
     cudaTriggerProgrammaticLaunchCompletion();
     long long task = gt;
     if (task < n_j) {
-      junction_task(nd, cur, (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
+      junction_task(nd, cur, b0 + (int)(task / nd.nj), (int)(task % nd.nj), log_slot);
     } else if (task < n_j + n_l) {
       task -= n_j;
-      leaf_task(nd, cur, (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
+      leaf_task(nd, cur, b0 + (int)(task / nd.nl), (int)(task % nd.nl), log_slot);
     }
   }
 }
@@ -1094,6 +1095,16 @@ struct af_net {
   bool pdl = true;                 // programmatic dependent launch of k_artery (AF_NO_PDL=1 disables)
   bool fused = false;              // af_net_step: set_bcs inside the artery CTAs (single networks)
   int boundary_block = 64;         // threads per CTA of k_boundary (AF_BOUNDARY_BLOCK overrides)
+  // Ensembles: the member range is cut into n_sub contiguous shares, each stepped on its own
+  // stream.  Members are independent, so the shares drift freely inside one af_net_step call
+  // and the boundary kernel of one share (latency / memory-bound, few warps) fills the machine
+  // under the artery kernel of another (FP64 / issue-bound) and under its tail wave.  The
+  // shares fork from and join the handle's stream at the ends of the call and around snapshots,
+  // so to the caller everything stays ordered on that one stream.
+  static const int kMaxSub = 4;
+  int n_sub = 1;
+  cudaStream_t sub[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
   int n_pending = 0;
 
@@ -1193,9 +1204,10 @@ extern "C" void af_desc_defaults(af_desc* d) {
 }
 
 template <int T>
-static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot, bool fused) {
+static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot, bool fused,
+                                 cudaStream_t stream) {
   if (fused && T >= 64) {
-    k_artery<T, (T >= 64)><<<count, T, n->artery_smem, n->stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
+    k_artery<T, (T >= 64)><<<count, T, n->artery_smem, stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
     return cudaGetLastError();
   }
   // programmatic stream serialisation: may start while the preceding kernel of the
@@ -1204,7 +1216,7 @@ static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_
   cfg.gridDim = dim3((unsigned)count);
   cfg.blockDim = dim3(T);
   cfg.dynamicSmemBytes = n->artery_smem;
-  cfg.stream = n->stream;
+  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = n->pdl ? 1 : 0;
@@ -1224,18 +1236,21 @@ static cudaError_t prepare_artery(af_net* n) {
 }
 
 static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot,
-                              bool fused = false) {
+                              bool fused = false, cudaStream_t stream = nullptr) {
+  if (!stream) stream = n->stream;
   switch (n->artery_threads) {
-    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot, fused);
-    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot, fused);
-    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot, fused);
-    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot, fused);
-    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused);
+    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot, fused, stream);
+    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot, fused, stream);
+    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot, fused, stream);
+    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot, fused, stream);
+    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused, stream);
   }
 }
 
-static cudaError_t run_boundary(const af_net* n, int log_slot) {
-  long long tasks = (long long)n->nd.nb * (n->nd.nj + n->nd.nl);
+static cudaError_t run_boundary(const af_net* n, int log_slot, int b0 = 0, int nbl = -1, cudaStream_t stream = nullptr) {
+  if (nbl < 0) nbl = n->nd.nb;
+  if (!stream) stream = n->stream;
+  long long tasks = (long long)nbl * (n->nd.nj + n->nd.nl);
   long long threads = tasks * n->boundary_lanes;
   int block = n->boundary_block;
   long long grid = (threads + block - 1) / block;
@@ -1243,15 +1258,15 @@ static cudaError_t run_boundary(const af_net* n, int log_slot) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(block);
-  cfg.stream = n->stream;
+  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = n->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (n->boundary_lanes == 32)
-    return cudaLaunchKernelEx(&cfg, k_boundary<true>, n->nd, n->cur, log_slot);
-  return cudaLaunchKernelEx(&cfg, k_boundary<false>, n->nd, n->cur, log_slot);
+    return cudaLaunchKernelEx(&cfg, k_boundary<true>, n->nd, n->cur, log_slot, b0, nbl);
+  return cudaLaunchKernelEx(&cfg, k_boundary<false>, n->nd, n->cur, log_slot, b0, nbl);
 }
 
 extern "C" int af_net_create(const af_desc* d, af_net** out) {
@@ -1401,6 +1416,24 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
     if ((a != 0 && art_jin[a] < 0) || (art_leaf[a] < 0 && art_jout[a] < 0)) n->fused = false;
   if (const char* env = getenv("AF_NO_FUSE")) if (atoi(env)) n->fused = false;
   if (const char* env = getenv("AF_NO_PDL")) if (atoi(env)) n->pdl = false;
+  // sub-streams for ensembles: every share must still fill the machine (148 SMs x 16 one-warp CTAs) twice over
+  if (n->boundary_lanes == 1) {
+    const long long ctas = (long long)nd.nb * nd.na, fill = 2LL * 148 * AF_T32_BLOCKS;
+    n->n_sub = ctas >= 4 * fill ? 4 : (ctas >= 2 * fill ? 2 : 1);
+    if (const char* env = getenv("AF_SUBSTREAMS")) {
+      int v = atoi(env);
+      if (v >= 1 && v <= af_net::kMaxSub) n->n_sub = v;
+    }
+    if (n->n_sub > nd.nb) n->n_sub = nd.nb;
+  }
+  if (n->n_sub > 1) {
+    cudaError_t es = cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming);
+    for (int k = 0; k < n->n_sub && es == cudaSuccess; ++k) {
+      es = cudaStreamCreateWithFlags(&n->sub[k], cudaStreamNonBlocking);
+      if (es == cudaSuccess) es = cudaEventCreateWithFlags(&n->ev_join[k], cudaEventDisableTiming);
+    }
+    if (es != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("sub-streams: ") + cudaGetErrorString(es)); }
+  }
   if (const char* env = getenv("AF_BOUNDARY_BLOCK")) {
     int v = atoi(env);
     if (v >= 32 && v <= 1024 && v % 32 == 0) n->boundary_block = v;
@@ -1431,6 +1464,11 @@ extern "C" void af_net_destroy(af_net* n) {
   cudaSetDevice(n->device);
   if (n->stream) cudaStreamSynchronize(n->stream);
   if (n->copy_stream) cudaStreamSynchronize(n->copy_stream);
+  for (int k = 0; k < af_net::kMaxSub; ++k) {
+    if (n->sub[k]) { cudaStreamSynchronize(n->sub[k]); cudaStreamDestroy(n->sub[k]); }
+    if (n->ev_join[k]) cudaEventDestroy(n->ev_join[k]);
+  }
+  if (n->ev_fork) cudaEventDestroy(n->ev_fork);
   for (auto& blk : n->allocs) af_net::release_block(n->device, blk.first, blk.second);
   for (cudaEvent_t ev : n->snap_event) cudaEventDestroy(ev);
   for (int k = 0; k < af_net::kRing; ++k) if (n->ring_done[k]) cudaEventDestroy(n->ring_done[k]);
@@ -1551,18 +1589,38 @@ static int take_snapshot(af_net* n, int64_t g) {
   return AF_OK;
 }
 
+// sub-streams: everything enqueued on the handle's stream so far happens before the shares go on ...
+static int fork_subs(af_net* n) {
+  AF_CUDA(cudaEventRecord(n->ev_fork, n->stream));
+  for (int k = 0; k < n->n_sub; ++k) AF_CUDA(cudaStreamWaitEvent(n->sub[k], n->ev_fork, 0));
+  return AF_OK;
+}
+// ... and the handle's stream continues after all of them
+static int join_subs(af_net* n) {
+  for (int k = 0; k < n->n_sub; ++k) {
+    AF_CUDA(cudaEventRecord(n->ev_join[k], n->sub[k]));
+    AF_CUDA(cudaStreamWaitEvent(n->stream, n->ev_join[k], 0));
+  }
+  return AF_OK;
+}
+
 extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
   int rc = check(n);
   if (rc) return rc;
   if (n_first < 0 || n_steps < 0) return fail(AF_EINVAL, "negative step range");
   if (n->n_pending) return fail(AF_ESTATE, "arteries with a pending solve: call af_artery_update first");
   const int Nt = n->nd.Nt;
+  const bool split = n->n_sub > 1 && n_steps > 0;
+  if (split && (rc = fork_subs(n))) return rc;
   for (int64_t g = n_first; g < n_first + n_steps; ++g) {
     int step = (int)(g % Nt);
     int64_t cycle = g / Nt;
-    if (n->max_snap && cycle >= n->first_cycle && n->mask[step]) {
+    if (n->max_snap && cycle >= n->first_cycle && n->mask[step] && n->n_snap < n->max_snap) {
+      // the dump kernels read every member: gather the shares, dump on the handle's stream, release them
+      if (split && (rc = join_subs(n))) return rc;
       rc = take_snapshot(n, g);
       if (rc) return rc;
+      if (split && (rc = fork_subs(n))) return rc;
     }
     if (n->ring && n->n_delivered < n->n_streamed && (g & 7) == 0) {
       rc = drain_ring(n, false, false);
@@ -1573,12 +1631,19 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     if (n->fused) {
       AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot, true));
       std::swap(n->nd.jx, n->nd.jx_next);
+    } else if (split) {
+      for (int k = 0; k < n->n_sub; ++k) {
+        const int b0 = (int)((long long)n->nd.nb * k / n->n_sub), b1 = (int)((long long)n->nd.nb * (k + 1) / n->n_sub);
+        AF_CUDA(run_boundary(n, log_slot, b0, b1 - b0, n->sub[k]));
+        AF_CUDA(run_artery(n, b0 * n->nd.na, (b1 - b0) * n->nd.na, inlet, log_slot, false, n->sub[k]));
+      }
     } else {
       AF_CUDA(run_boundary(n, log_slot));
       AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot));
     }
     n->cur ^= 1;
   }
+  if (split && (rc = join_subs(n))) return rc;
   return AF_OK;
 }
 

@@ -372,3 +372,39 @@ def test_tapered_vessels_in_a_batch():
         np.testing.assert_array_equal(q[m], q1[0])
     assert not np.array_equal(A[0], A[1])
     assert int(np.bitwise_or.reduce(batch.get_flags())) & 9 == 0
+
+
+def test_ensemble_substreams_equal_single_stream(monkeypatch):
+    """Large ensembles are stepped as up to four member shares on their own
+    streams (AF_SUBSTREAMS), forked from / joined to the handle's stream around
+    af_net_step and around snapshots.  Members are independent, so the result
+    must be bitwise the one of a single stream -- state, holders, counters,
+    snapshots and the per-step logs."""
+    from bloodflow_b200 import _ffi
+    from bloodflow_b200.ensemble import EnsembleNetwork
+    from bloodflow_b200.synthetic import tree_param
+
+    def run(subs):
+        monkeypatch.setenv('AF_SUBSTREAMS', str(subs))
+        ens = EnsembleNetwork(tree_param(3, Nx=20, Nt=400, Nt_store=40), 1500)   # 10 500 tasks: thread-per-task kernel
+        dev = ens.dev
+        dev.set_store(ens.nominal.store_mask(), 0, 6, _ffi.AF_STORE_OUTLET_PRESSURE | _ffi.AF_STORE_FLOW)
+        dev.set_counter_log(45)
+        for first, n in ((0, 13), (13, 1), (14, 31)):
+            dev.step(first, n)
+        out = (dev.get_state(), dev.get_bc(), dev.get_dex(), dev.get_junction_x(), dev.get_totals(),
+               dev.fetch_counter_log(), dev.fetch_snapshots())
+        dev.close()
+        return out
+
+    one, four, three = run(1), run(4), run(3)
+    for other in (four, three):
+        for a, b in zip(one[0], other[0]):
+            np.testing.assert_array_equal(a, b)
+        for k in (1, 2, 3, 4):
+            np.testing.assert_array_equal(one[k], other[k])
+        for a, b in zip(one[5], other[5]):
+            np.testing.assert_array_equal(a, b)
+        assert list(one[6]['step']) == list(other[6]['step']) == [0, 10, 20, 30, 40]
+        for key in ('flow', 'outlet_pressure'):
+            np.testing.assert_array_equal(one[6][key], other[6][key])
