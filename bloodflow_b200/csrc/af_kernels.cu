@@ -780,8 +780,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       for (int sdist = 1; sdist < T; sdist *= 2) {
         park(buf, T, tid, make_elim(rd));
         cta_sync<T>();
-        if (tid >= sdist) apply_left(rd, unpark(buf, T, tid - sdist));
-        if (tid + sdist < T) apply_right(rd, unpark(buf, T, tid + sdist));
+        const bool more = 2 * sdist < T;       // the last step leaves rows that are never coupled again
+        if (tid >= sdist) apply_left(rd, unpark(buf, T, tid - sdist), more);
+        if (tid + sdist < T) apply_right(rd, unpark(buf, T, tid + sdist), more);
         cta_sync<T>();
       }
       double inv[4];

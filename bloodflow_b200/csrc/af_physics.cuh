@@ -1048,21 +1048,27 @@ AF_HD void neg_mul2(const double a[4], const double b[4], double o[4]) {
 }
 
 // eliminate the LEFT neighbour of row w (coupled through w.lo)
-AF_HD void apply_left(Row& w, const Elim& e) {
+// `couple` = false skips the new coupling block (the last step of a reduction, after
+// which only the diagonal block and the right-hand side are read).
+AF_HD void apply_left(Row& w, const Elim& e, bool couple = true) {
   sub_mul2(w.dg, w.lo, e.Q);
   sub_mulv(w.r, w.lo, e.g);
-  double m[4];
-  neg_mul2(w.lo, e.P, m);
-  w.lo[0] = m[0]; w.lo[1] = m[1]; w.lo[2] = m[2]; w.lo[3] = m[3];
+  if (couple) {
+    double m[4];
+    neg_mul2(w.lo, e.P, m);
+    w.lo[0] = m[0]; w.lo[1] = m[1]; w.lo[2] = m[2]; w.lo[3] = m[3];
+  }
 }
 
 // eliminate the RIGHT neighbour of row w (coupled through w.up)
-AF_HD void apply_right(Row& w, const Elim& e) {
+AF_HD void apply_right(Row& w, const Elim& e, bool couple = true) {
   sub_mul2(w.dg, w.up, e.P);
   sub_mulv(w.r, w.up, e.g);
-  double m[4];
-  neg_mul2(w.up, e.Q, m);
-  w.up[0] = m[0]; w.up[1] = m[1]; w.up[2] = m[2]; w.up[3] = m[3];
+  if (couple) {
+    double m[4];
+    neg_mul2(w.up, e.Q, m);
+    w.up[0] = m[0]; w.up[1] = m[1]; w.up[2] = m[2]; w.up[3] = m[3];
+  }
 }
 
 AF_HD void back_sub(const Elim& e, const double xl[2], const double xr[2], double x[2]) {
