@@ -319,7 +319,7 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   cL.f = ves.fL; cL.A0 = ves.A0L;
   double AL, qL;
   interp_state(A, q, nd.Nx, ves.dx, L, AL, qL);
-  const double dex = (1.0 + nd.cfl_margin) * dt / cfl_term(ves, cL, AL, qL);
+  const double dex = AF_DIV((1.0 + nd.cfl_margin) * dt, cfl_term(ves, cL, AL, qL));
   // stencil point of this lane and its flux / source (an:385-390)
   const double xk = L - (double)(2 - k) * dex;
   double Ak, qk;
@@ -330,7 +330,7 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   const double xn = __shfl_down_sync(FULL, xk, 1), An = __shfl_down_sync(FULL, Ak, 1);
   const double qn = __shfl_down_sync(FULL, qk, 1), Fn = __shfl_down_sync(FULL, Fk, 1);
   const double Sn = __shfl_down_sync(FULL, Sk, 1);
-  const double rr = dt / (xn - xk);
+  const double rr = AF_DIV(dt, xn - xk);
   const double Ah = (Ak + An) / 2.0 - rr * (qn - qk);
   const double qh = (qk + qn) / 2.0 - rr * (Fn - Fk) + dt / 4.0 * (Sk + Sn);
   const double xh = L - (1.5 - (double)k) * dex;       // L-1.5dex, L-0.5dex
@@ -341,7 +341,7 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   const double F10 = __shfl_sync(FULL, Fh, 1), S10 = __shfl_sync(FULL, Sh, 1);
   const double q1 = __shfl_sync(FULL, qk, 1);
   const double A0s = __shfl_sync(FULL, Ak, 2), q0s = __shfl_sync(FULL, qk, 2);
-  const double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
+  const double qm1 = q1 - AF_DIV(dt, dex) * (F10 - F21) + dt / 2.0 * (S10 + S21);
   WkResult r;
   r.A_out = 0.0; r.dex = dex; r.its = 0;
   if (lane != 0) return r;

@@ -170,7 +170,7 @@ AF_HD double cfl_term(const Vessel& v, const Coef& c, double A, double q) {
 }
 
 AF_HD double outlet_pressure(const Vessel& v, double A) {   // ar:285-301
-  return v.p0 + v.fL * (1.0 - sqrt(v.A0L / A));
+  return v.p0 + v.fL * (1.0 - af_sqrt_pos(v.A0L) * af_rsqrt_fast(A));
 }
 
 // ---------------------------------------------------------------------------
@@ -193,12 +193,14 @@ AF_HD WkResult windkessel_picard(const Vessel& v, double dt, double dex, double 
   // with the p-independent terms folded:  Am0 = K2 - K3 p,  p = K4 - K5 rsqrt(Am0).
   // Two FMAs and one reciprocal square root per iteration on the serial chain;
   // rounding differs from the reference's expression order by a few ulp.
-  const double c_pn = dt / R1 / R2 / CT * pn;
-  const double c_q = dt * (R1 + R2) / R1 / R2 / CT * q0s;
-  const double dtdex = dt / dex;
-  const double K3 = dtdex / R1;
+  // the three reciprocals are independent (the reference divides in sequence)
+  const double i_rrc = af_rcp_fast(R1 * R2 * CT), i_r1 = af_rcp_fast(R1);
+  const double c_pn = dt * i_rrc * pn;
+  const double c_q = dt * (R1 + R2) * i_rrc * q0s;
+  const double dtdex = AF_DIV(dt, dex);
+  const double K3 = dtdex * i_r1;
   const double K2 = A0s - dtdex * (q0s + c_pn - c_q - qm1) + K3 * pn;
-  const double K5 = v.fL * sqrt(v.A0L);
+  const double K5 = v.fL * af_sqrt_pos(v.A0L);
   const double K4 = v.p0 + v.fL;
   double p = pn, p1 = pn, p2 = pn, p3 = pn;   // p_k, p_{k-1}, p_{k-2}, p_{k-3}
   double Am0 = A0s, Am1 = A0s, Am2 = A0s;     // Am_k, Am_{k-1}, Am_{k-2}
@@ -238,7 +240,7 @@ AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int
   cL.f = v.fL; cL.A0 = v.A0L;
   double AL, qL;
   interp_state(A, q, Nx, v.dx, L, AL, qL);
-  double dex = (1.0 + margin) * dt / cfl_term(v, cL, AL, qL);       // adjust_dex (ar:349-365)
+  double dex = AF_DIV((1.0 + margin) * dt, cfl_term(v, cL, AL, qL));       // adjust_dex (ar:349-365)
   double x2 = L - 2.0 * dex, x1 = L - dex, x0 = L;
   double x21 = L - 1.5 * dex, x10 = L - 0.5 * dex;
   double A2, q2, A1, q1, A0s, q0s;
@@ -251,7 +253,7 @@ AF_HD WkResult windkessel(const Vessel& v, const double* A, const double* q, int
   Coef c21 = coef_at(v, x21), c10 = coef_at(v, x10);
   double F21 = bc_flux2(c21, Ah21, qh21), S21 = bc_source2(v, c21, Ah21, qh21);
   double F10 = bc_flux2(c10, Ah10, qh10), S10 = bc_source2(v, c10, Ah10, qh10);
-  double qm1 = q1 - dt / dex * (F10 - F21) + dt / 2.0 * (S10 + S21);
+  double qm1 = q1 - AF_DIV(dt, dex) * (F10 - F21) + dt / 2.0 * (S10 + S21);
   return windkessel_picard(v, dt, dex, A0s, q0s, qm1, R1, R2, CT, k_max, tol);
 }
 
