@@ -8,7 +8,11 @@
 //   dex[nb*na], jx[nb*nj*18]       boundary step, junction unknowns (warm start)
 //   cellcoef[nt][9][S]             Gauss-point coefficients, tapered arteries only
 // One launch of k_boundary (all junctions + leaves of all networks) and one of
-// k_artery (one CTA per artery) make a time step; see DESIGN.md.
+// k_artery (one CTA per artery) make a time step; the two are chained by
+// programmatic dependent launch in both directions.  Large ensembles are cut into
+// member shares that run this chain on their own forked streams (af_net_step).
+// Host side: the C ABI, a pinned ring that streams snapshots out during the loop,
+// and an exact-size cache of released device / pinned blocks.  See DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
