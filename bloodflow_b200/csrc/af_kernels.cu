@@ -230,7 +230,7 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v = lane % 3;
-  const int ba = b * nd.na + ia[v];
+  const int ba = b * nd.na + (v == 0 ? ia[0] : (v == 1 ? ia[1] : ia[2]));
   const size_t off = (size_t)ba * nd.S;
   const double* A = nd.A[cur] + off;
   const double* q = nd.q[cur] + off;
@@ -251,7 +251,12 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   int k = 0;
   bool singular = false;
   for (; k < nd.junction_k_max; ++k) {
-    const double xv[6] = {x[3 * v], x[3 * v + 1], x[3 * v + 2], x[9 + 3 * v], x[10 + 3 * v], x[11 + 3 * v]};
+    // this lane's six unknowns, picked by selects: indexing x[] with the run-time v would
+    // put the 18 unknowns into local memory for the whole Newton loop
+#define AF_PICK3(a, b, c) (v == 0 ? (a) : (v == 1 ? (b) : (c)))
+    const double xv[6] = {AF_PICK3(x[0], x[3], x[6]),   AF_PICK3(x[1], x[4], x[7]),    AF_PICK3(x[2], x[5], x[8]),
+                          AF_PICK3(x[9], x[12], x[15]), AF_PICK3(x[10], x[13], x[16]), AF_PICK3(x[11], x[14], x[17])};
+#undef AF_PICK3
     JVesselLin mine, l[3];
     jvessel_linearise(jv, xv, mine);
 #pragma unroll
@@ -382,7 +387,7 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl) {
     if (is_junction) {
       b = b0 + (int)(task / nd.nj); j = (int)(task % nd.nj);
       ia[0] = nd.j_p[j]; ia[1] = nd.j_d1[j]; ia[2] = nd.j_d2[j];
-      ba = b * nd.na + ia[v];
+      ba = b * nd.na + (v == 0 ? ia[0] : (v == 1 ? ia[1] : ia[2]));
     } else if (is_leaf) {
       task -= n_j;
       b = b0 + (int)(task / nd.nl); l = (int)(task % nd.nl);
