@@ -269,9 +269,10 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
     }
     double y[18];
     junction_gather(l, x, y);
-    double nrm = 0.0;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;      // three partial sums: a third of the serial FMA chain
 #pragma unroll
-    for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
+    for (int i = 0; i < 6; ++i) { n0 = fma(y[i], y[i], n0); n1 = fma(y[6 + i], y[6 + i], n1); n2 = fma(y[12 + i], y[12 + i], n2); }
+    const double nrm = (n0 + n1) + n2;
     if (nrm < nd.junction_tol * nd.junction_tol) break;      // ||y|| < tol (an:684), no sqrt on the chain
     if (junction_update(l, dtdex_p, dtdex_d1, y)) { singular = true; break; }
 #pragma unroll

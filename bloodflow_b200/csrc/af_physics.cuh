@@ -706,9 +706,10 @@ AF_HD int junction_newton_fast(const JVessel jv[3], double* x, int k_max, double
       jvessel_linearise(jv[v], xv, l[v]);
     }
     junction_gather(l, x, y);
-    double nrm = 0.0;
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;      // same three partial sums as the warp version
 #pragma unroll
-    for (int i = 0; i < 18; ++i) nrm += y[i] * y[i];
+    for (int i = 0; i < 6; ++i) { n0 = fma(y[i], y[i], n0); n1 = fma(y[6 + i], y[6 + i], n1); n2 = fma(y[12 + i], y[12 + i], n2); }
+    const double nrm = (n0 + n1) + n2;
     if (nrm < tol * tol) break;          // ||y|| < tol (an:684) without the square root on the serial chain
     if (junction_update(l, jv[0].dtdex, jv[1].dtdex, y)) return -1;
 #pragma unroll
