@@ -380,7 +380,11 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl) {
     // Topology and vessel constants do not depend on the state: fetch them first,
     // they arrive while this kernel -- which may have been made resident under
     // the artery kernel of the previous step (programmatic dependent launch) --
-    // waits for that kernel's Un.
+    // waits for that kernel's Un.  ONLY constants may be read up here: the artery
+    // kernel triggers at its very start, possibly while the boundary kernel of the
+    // previous step is still running, so two generations of this kernel can be
+    // resident together and jx / bc / dex of the previous step may not be final yet
+    // (measured: fetching the Newton warm start here broke bitwise reproducibility).
     long long task = gt >> 5;
     const int v = (threadIdx.x & 31) % 3;
     int b = 0, j = 0, l = 0, ba = 0, ia[3] = {0, 0, 0};
