@@ -246,7 +246,7 @@ class OracleArtery(object):
                 + (2 * np.sqrt(A) * (np.sqrt(np.pi) * f + np.sqrt(A0) * dfdr)
                    - A * dfdr) * drdx)
 
-    def assemble(self, U, jacobian=False):
+    def assemble(self, U, jacobian=False, apply_bc=True):
         """Residual (Nx+1, 2) and, optionally, the 2x2-block tridiagonal
         Jacobian (lower, diag, upper: each (Nx+1, 2, 2); block[r, c] is
         d R[(node, r)] / d U[(neighbour, c)]) of the theta-scheme weak form,
@@ -317,7 +317,7 @@ class OracleArtery(object):
                                              + fv * A0v / (2 * np.sqrt(A0v * Ae)))
                 Dg[node, 1, 1] += dt * th * 2 * q / Ae
         # [3P] DirichletBC: residual row := U_dof - g ; Jacobian row := identity
-        for node, comp, g in self._dirichlet():
+        for node, comp, g in (self._dirichlet() if apply_bc else ()):
             R[node, comp] = U[node, comp] - g
             if jacobian:
                 Lo[node, comp, :] = 0

@@ -518,6 +518,39 @@ void orc_set_state(orc_net* n, const double* A, const double* q) {
   size_t b = (size_t)n->na * n->np * sizeof(double);
   memcpy(n->A, A, b); memcpy(n->q, q, b); memcpy(n->UA, A, b); memcpy(n->Uq, q, b);
 }
+void orc_set_bc(orc_net* n, const double* bc) { memcpy(n->bc, bc, (size_t)n->na * 4 * sizeof(double)); }
+/* the pending iterate U of every artery (== Un between steps) */
+void orc_get_pending(const orc_net* n, double* A, double* q) {
+  memcpy(A, n->UA, (size_t)n->na * n->np * sizeof(double));
+  memcpy(q, n->Uq, (size_t)n->na * n->np * sizeof(double));
+}
+/* residual R[2*np] and Jacobian as 2x2 blocks J[3][np][2][2] (lower, diagonal, upper) of artery a
+ * at the iterate (UA, Uq) with the current Un and BC holders, Dirichlet rows applied */
+void orc_artery_assemble(const orc_net* n, int a, const double* UA, const double* Uq, double* R, double* J) {
+  int np = n->np;
+  double* Mb = (double*)malloc((size_t)2 * np * BW * sizeof(double));
+  assemble(n, a, UA, Uq, R, Mb);
+  memset(J, 0, (size_t)3 * np * 4 * sizeof(double));
+  for (int j = 0; j < np; ++j)
+    for (int b = 0; b < 3; ++b) {
+      int jc = j + b - 1;
+      if (jc < 0 || jc >= np) continue;
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c) J[(((size_t)b * np + j) * 2 + r) * 2 + c] = MB(2 * j + r, 2 * jc + c);
+    }
+  free(Mb);
+}
+/* Artery.solve() of one artery with at most max_it linear solves (no update_solution); returns the count */
+int orc_artery_solve(orc_net* n, int a, int max_it) {
+  int np = n->np, keep = n->max_it, failed = n->failed;
+  double* R = (double*)malloc(2 * np * sizeof(double));
+  double* Mb = (double*)malloc((size_t)2 * np * BW * sizeof(double));
+  n->max_it = max_it;
+  artery_solve(n, a, R, Mb);
+  n->max_it = keep; n->failed = failed;
+  free(R); free(Mb);
+  return n->art_its[a];
+}
 void orc_get_x(const orc_net* n, double* x) { memcpy(x, n->x, (size_t)n->nj * 18 * sizeof(double)); }
 void orc_get_bc(const orc_net* n, double* bc) { memcpy(bc, n->bc, (size_t)n->na * 4 * sizeof(double)); }
 void orc_get_totals(const orc_net* n, long long* t) { memcpy(t, n->tot, 3 * sizeof(long long)); }

@@ -35,7 +35,11 @@ def lib():
         _lib.orc_step.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, _ip, _ip]
         for name in ('orc_get_state', 'orc_set_state'):
             getattr(_lib, name).argtypes = [ctypes.c_void_p, _dp, _dp]
-        for name in ('orc_get_x', 'orc_get_bc', 'orc_get_pressure'):
+        _lib.orc_get_pending.argtypes = [ctypes.c_void_p, _dp, _dp]
+        _lib.orc_artery_assemble.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, _dp]
+        _lib.orc_artery_solve.restype = ctypes.c_int
+        _lib.orc_artery_solve.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        for name in ('orc_get_x', 'orc_get_bc', 'orc_get_pressure', 'orc_set_bc'):
             getattr(_lib, name).argtypes = [ctypes.c_void_p, _dp]
         _lib.orc_get_totals.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
         _lib.orc_max_threads.restype = ctypes.c_int
@@ -98,6 +102,32 @@ class COracle(object):
     def set_state(self, A, q):
         A, q = _d(A), _d(q)
         lib().orc_set_state(self._h, A.ctypes.data_as(_dp), q.ctypes.data_as(_dp))
+
+    def pending(self):
+        A, q = np.zeros((self.na, self.np)), np.zeros((self.na, self.np))
+        lib().orc_get_pending(self._h, A.ctypes.data_as(_dp), q.ctypes.data_as(_dp))
+        return A, q
+
+    def set_bc(self, bc):
+        bc = _d(bc)
+        assert bc.shape == (self.na, 4)
+        lib().orc_set_bc(self._h, bc.ctypes.data_as(_dp))
+
+    def bc(self):
+        bc = np.zeros((self.na, 4))
+        lib().orc_get_bc(self._h, bc.ctypes.data_as(_dp))
+        return bc
+
+    def artery_assemble(self, a, UA, Uq):
+        """Residual (np, 2) and Jacobian blocks (3, np, 2, 2), Dirichlet rows applied."""
+        UA, Uq = _d(UA), _d(Uq)
+        R, J = np.zeros((self.np, 2)), np.zeros((3, self.np, 2, 2))
+        lib().orc_artery_assemble(self._h, a, UA.ctypes.data_as(_dp), Uq.ctypes.data_as(_dp),
+                                  R.ctypes.data_as(_dp), J.ctypes.data_as(_dp))
+        return R, J
+
+    def artery_solve(self, a, max_it=1000):
+        return lib().orc_artery_solve(self._h, a, max_it)
 
     def x(self):
         x = np.zeros((self.nj, 18))

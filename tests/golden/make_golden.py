@@ -8,21 +8,26 @@ The unmodified reference modules are imported under ``dolfin_standin`` (see its
 docstring).  All boundary-condition arithmetic, the time loop, the parameter
 handling and the initial conditions that end up in the fixtures are computed by
 reference code (``arteryfe/artery_network.py``, ``artery.py``, ``utils.py``,
-``param_parser.py``).  The single substituted piece is FEniCS' per-artery
-variational solve ([3P], un-vendored), for which the numpy oracle's restatement
-is plugged in -- so fixtures that depend on states after the first step
-("hybrid" runs) pin the reference's own code GIVEN that restatement.
+``param_parser.py``).  FEniCS' per-artery variational solve ([3P], un-vendored)
+is performed on the reference's OWN ``variational_form`` / ``derivative(F, U)``
+objects (artery.py:191-238) by the generic assembler + NewtonSolver loop of
+``ufl_live.py``; the repo's oracle is not involved in producing any fixture.
 
 Fixtures (numpy .npz, a few hundred kB in total):
 
 * setup_<case>.npz     nondimensional parameters, T, dt, q_ins, per-artery
                        constants, Expression samples, initial state, x0
-* bc_<case>.npz        at steps k in BC_STEPS of a hybrid run: Un of every
+* bc_<case>.npz        at steps k in BC_STEPS of the reference loop: Un of every
                        artery, dex, and for every junction problem_function(x),
                        jacobian(x), newton(x) / for every leaf windkessel();
                        plus flux/source/compute_U_half/CFL_term samples
+* fem_<case>.npz       at the same steps, per artery: iterate U0 (= Un), Dirichlet
+                       values, residual and block-tridiagonal Jacobian before
+                       (``*_raw``) and after the Dirichlet rows at the first two
+                       Newton iterates, the updates dU0/dU1, the converged
+                       iterate and the number of linear solves
 * run_<case>.npz       stored flow/area/pressure of the reference's own
-                       ArteryNetwork.solve() loop (hybrid), with times
+                       ArteryNetwork.solve() loop, with times and Newton counts
 """
 import contextlib
 import io
@@ -44,7 +49,6 @@ dolfin_standin.install()
 sys.path.insert(0, REFERENCE)
 
 import arteryfe as ref  # noqa: E402  (the reference package)
-from oracle import arteryfe_oracle as ao  # noqa: E402
 
 INLET = os.path.join(ROOT, 'data', 'example_inlet.csv')
 
@@ -130,32 +134,15 @@ def reference_network(cfg):
     return ref.ArteryNetwork(param)
 
 
-class Twin(object):
-    """Routes the stand-in's NonlinearVariationalSolver.solve() of reference
-    artery ``ra`` to the oracle artery built from the same cfg."""
+class SolveLog(object):
+    """Observer of the stand-in's NonlinearVariationalSolver.solve(): logs the
+    number of linear solves of every per-artery Newton solve."""
 
-    def __init__(self, ref_net, cfg):
-        self.ref_net = ref_net
-        self.orc = ao.network_from_cfg(cfg)
-        self.by_U = {id(a.U): a for a in ref_net.arteries if a is not None}
+    def __init__(self):
         self.its = []
 
-    def __call__(self, problem):
-        ra = self.by_U[id(problem.U)]
-        oa = self.orc.arteries[ra.i]
-        oa._Un[:] = ra.Un.values
-        oa._U[:] = ra.U.values
-        if ra.root:
-            oa.q_in = ra.q_in
-        else:
-            oa.U_in = ra.U_in
-        if ra.leaf:
-            oa.A_out = ra.A_out
-        else:
-            oa.U_out = ra.U_out
-        oa.solve()
-        ra.U.values[:] = oa._U
-        self.its.append(oa.newton_its)
+    def __call__(self, problem, its):
+        self.its.append(its)
 
 
 def arteries_of(net):
@@ -191,9 +178,9 @@ def golden_setup(net, case):
     return d
 
 
-def golden_bc(net, twin):
+def golden_bc(net):
     """Reference BC functions evaluated on the states of a hybrid run."""
-    d = {}
+    d, fem = {}, {}
     Nt = net.geo['Nt']
     arts = arteries_of(net)
     net.define_x()                      # what solve() does first (artery_network.py:874)
@@ -235,13 +222,27 @@ def golden_bc(net, twin):
             d[tag + 'leaf_dex'] = np.array(wdex)
         # advance one step exactly like the loop body artery_network.py:916-944
         net.set_bcs(net.q_ins[(n + 1) % Nt])
-        for a in arts:
+        for k, a in enumerate(arts):
+            if n in BC_STEPS:
+                rec = dolfin_standin.record_next = {}
             a.solve()
+            if n in BC_STEPS:
+                bc4 = np.full(4, np.nan)            # A_in, q_in, A_out, q_out (NaN: no Dirichlet row)
+                for node, comp, g in rec.pop('bc_rows'):
+                    bc4[(0 if node == 0 else 2) + int(comp)] = g
+                rec['bc4'] = bc4
+                for missing, like in (('J1_raw', 'J0_raw'), ('J1', 'J0'), ('dU1', 'dU0'),
+                                      ('U1', 'U0'), ('R1_raw', 'R0'), ('R1', 'R0')):
+                    if missing not in rec:          # the solve stopped before that iterate existed
+                        rec[missing] = np.full_like(rec[like], np.nan)
+                for key, val in rec.items():
+                    fem.setdefault('s%d_%s' % (n, key), []).append(val)
             a.update_solution()
-    return d
+    fem = {key: np.array(val) for key, val in fem.items()}
+    return d, fem
 
 
-def golden_run(net, twin):
+def golden_run(net, log):
     dolfin_standin.XDMFFile.written.clear()
     with contextlib.redirect_stdout(io.StringIO()):
         net.solve()
@@ -255,7 +256,7 @@ def golden_run(net, twin):
             d['t'] = np.array([t for t, _ in rec])
         d[field] = np.swapaxes(np.array(rows), 0, 1)       # [snapshot, artery, node]
     d['x_final'] = net.x.copy()
-    d['artery_its'] = np.array(twin.its).reshape(-1, len(arteries_of(net)))
+    d['artery_its'] = np.array(log.its).reshape(-1, len(arteries_of(net)))
     return d
 
 
@@ -269,12 +270,13 @@ def main():
         np.savez_compressed(os.path.join(HERE, 'setup_%s.npz' % case),
                             **golden_setup(reference_network(cfg), case))
         net = reference_network(cfg)
-        dolfin_standin.artery_solve_callback = Twin(net, cfg)
-        np.savez_compressed(os.path.join(HERE, 'bc_%s.npz' % case),
-                            **golden_bc(net, dolfin_standin.artery_solve_callback))
+        dolfin_standin.solve_observer = None
+        bc, fem = golden_bc(net)
+        np.savez_compressed(os.path.join(HERE, 'bc_%s.npz' % case), **bc)
+        np.savez_compressed(os.path.join(HERE, 'fem_%s.npz' % case), **fem)
         net = reference_network(cfg)
-        twin = dolfin_standin.artery_solve_callback = Twin(net, cfg)
-        np.savez_compressed(os.path.join(HERE, 'run_%s.npz' % case), **golden_run(net, twin))
+        log = dolfin_standin.solve_observer = SolveLog()
+        np.savez_compressed(os.path.join(HERE, 'run_%s.npz' % case), **golden_run(net, log))
         open(cfg, 'w').write(text.replace(INLET, 'data/example_inlet.csv').replace(tmp, 'output/golden'))
         print('wrote fixtures for', case)
 

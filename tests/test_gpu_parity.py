@@ -84,11 +84,56 @@ def test_boundary_functions_match_reference(case, step):
                                rtol=1e-13)
 
 
+def _device_like(an, **constants):
+    """A second device handle of the same network with other solver constants."""
+    from bloodflow_b200.engine import DeviceNetwork
+    d = an._description
+    return DeviceNetwork(
+        d['Nx'], d['Nt'], d['theta'], d['dt'], d['junctions'], d['leaves'],
+        k1=d['k1'], k2=d['k2'], k3=d['k3'], rho=d['rho'], Re=d['Re'], db=d['db'], p0=d['p0'],
+        Ru=d['Ru'][None], Rd=d['Rd'][None], L=d['L'][None], q0=d['q0'][None],
+        R1=d['R1'][None], R2=d['R2'][None], CT=d['CT'][None], q_ins=d['q_ins'], **constants)
+
+
 @pytest.mark.parametrize('case', CASES)
-def test_time_loop_matches_reference_hybrid(case):
-    """Whole device-resident loop against the reference's own solve() loop
-    (its FEniCS solve replaced by the oracle restatement, see make_golden.py):
-    every stored A, q, p within 1e-9, same artery Newton counts."""
+def test_artery_solve_matches_reference_form(case):
+    """af_artery_solve (k_artery: assembly + Dirichlet rows + block-tridiagonal solve + Newton control)
+    against fem_<case>.npz, i.e. against the reference's own variational_form text
+    (artery.py:191-230) and derivative(F, U) (artery.py:238) assembled by the generic assembler of
+    tests/golden/ufl_live.py: the iterate after ONE linear solve and the converged iterate to 1e-11,
+    the number of linear solves exactly."""
+    g = np.load(os.path.join(GOLDEN, 'fem_%s.npz' % case))
+    an = _facade(case)
+    one = _device_like(an, newton_max_it=1)
+    for s in BC_STEPS:
+        tag = 's%d_' % s
+        U0 = g[tag + 'U0']
+        for dev, key in ((one, 'U1'), (an._dev, 'U_final')):
+            dev.set_state(U0[None, :, :, 0], U0[None, :, :, 1])
+            dev.set_bc(np.nan_to_num(g[tag + 'bc4'])[None])
+            its = []
+            for k in range(dev.na):
+                dev.artery_solve(k)
+                its.append(dev.get_counters()[0][0, k])
+                dev.artery_update(k)
+            A, q = dev.get_state()
+            np.testing.assert_allclose(A[0], g[tag + key][:, :, 0], rtol=1e-11, err_msg=key)
+            np.testing.assert_allclose(q[0], g[tag + key][:, :, 1], rtol=1e-11, atol=1e-13, err_msg=key)
+            if key == 'U_final':
+                np.testing.assert_array_equal(its, g[tag + 'its'])
+                # the Newton update itself (not just the iterate): dU0 + dU1 to 1e-9 of its size
+                dU = g[tag + 'U0'] - g[tag + 'U_final']
+                got = np.stack([U0[:, :, 0] - A[0], U0[:, :, 1] - q[0]], axis=-1)
+                np.testing.assert_allclose(got, dU, rtol=0, atol=1e-9 * np.abs(dU).max())
+    one.close()
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_time_loop_matches_reference_loop(case):
+    """Whole device-resident loop against the reference's own solve() loop, whose
+    per-artery variational solve is the reference's form text assembled by
+    tests/golden/ufl_live.py (see make_golden.py; generic FEniCS machinery is the
+    only [3P] part left): every stored A, q, p within 1e-9, same artery Newton counts."""
     g = np.load(os.path.join(GOLDEN, 'run_%s.npz' % case))
     an = _facade(case)
     n_steps = an.geo['Nt'] * an.geo['N_cycles']

@@ -28,7 +28,7 @@ def test_c_oracle_matches_numpy_oracle(case, steps):
 
 
 def test_c_oracle_matches_reference_run():
-    """Full hybrid golden run of case c2 (500 steps, reference's own loop)."""
+    """Full golden run of case c2 (500 steps, reference's own loop)."""
     g = np.load(os.path.join(GOLDEN, 'run_c2.npz'))
     cfg = os.path.join(GOLDEN, 'golden_c2.cfg')
     net = ao.network_from_cfg(cfg)

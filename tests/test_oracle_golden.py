@@ -1,6 +1,6 @@
 """The oracle against the golden vectors produced by the REFERENCE's own code
 (tests/golden/make_golden.py): host set-up, every boundary-condition function
-of the hot path, and the full time loop (hybrid run, see make_golden.py)."""
+of the hot path, and the full time loop (reference loop on the live form, see make_golden.py)."""
 import os
 
 import numpy as np
@@ -81,7 +81,7 @@ def test_boundary_functions_match_reference(case, step):
 
 
 @pytest.mark.parametrize('case', ('c1',))
-def test_time_loop_matches_reference_hybrid(case):
+def test_time_loop_matches_reference_loop(case):
     """Oracle solve() against the reference's own ArteryNetwork.solve() loop
     (BCs, dump rule, time accumulation by reference code; per-artery FEM solve
     by the oracle restatement)."""
