@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get('ARTERYFE_B200_LIB') or os.path.join(_HERE, 'csrc', 'l
 AF_ABI_VERSION = 1
 AF_OK, AF_EINVAL, AF_ENODEVICE, AF_ECUDA, AF_ENOMEM, AF_ESTATE = 0, -1, -2, -3, -4, -5
 AF_FLAG_ARTERY_NOCONV, AF_FLAG_JUNCTION_KMAX, AF_FLAG_PICARD_KMAX = 1, 2, 4
-AF_FLAG_NONFINITE, AF_FLAG_SINGULAR = 8, 16
+AF_FLAG_NONFINITE, AF_FLAG_SINGULAR, AF_FLAG_PICARD_CYCLE = 8, 16, 32
 AF_STORE_FLOW, AF_STORE_AREA, AF_STORE_PRESSURE, AF_STORE_OUTLET_PRESSURE = 1, 2, 4, 8
 
 c_int, c_i32, c_i64, c_dbl = ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
@@ -54,6 +54,11 @@ PROTOTYPES = {
     'af_release_cached_memory': (c_int, []),
     'af_net_step': (c_int, [Handle, c_i64, c_i64]),
     'af_net_sync': (c_int, [Handle]),
+    'af_net_failed_step': (c_int, [Handle, P_i64]),
+    'af_net_clear_flags': (c_int, [Handle]),
+    'af_net_outlet_moments_d': (c_int, [Handle, ctypes.POINTER(ctypes.c_void_p), P_i32]),
+    'af_moments_combine_d': (c_int, [c_i32, ctypes.c_void_p, ctypes.c_void_p, c_i32, c_i32, ctypes.c_void_p]),
+    'af_junction_cfl_min': (c_int, [Handle, c_i32, c_i32, P_dbl]),
     'af_net_set_store': (c_int, [Handle, P_u8, c_i32, c_i32, c_i32]),
     'af_net_set_store_host': (c_int, [Handle, P_dbl, P_dbl, P_dbl, P_dbl]),
     'af_net_snapshot_count': (c_int, [Handle, P_i32]),

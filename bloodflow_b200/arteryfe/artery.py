@@ -7,6 +7,8 @@ CUDA library.  An Artery built on its own (as the reference's unit tests do)
 owns a private one-vessel device network; inside an ArteryNetwork it is
 attached to the network's handle.
 """
+import math
+
 import numpy as np
 
 from .. import _ffi
@@ -99,14 +101,14 @@ class Artery(object):
         self.dx = self._L / self.Nx
         self.dt = self.T / self.Nt
         self._dex_host = self.dx
-        self.db = np.sqrt(p['nu'] * self.T / 2 / np.pi)
+        self.db = math.sqrt(p['nu'] * self.T / 2 / np.pi)      # ar:100 (IEEE sqrt, same bits as np.sqrt)
         if self.leaf and self._Rd == 1:
             self._Rd = p['R_term']
 
     def define_solution(self, q0, theta=0.5, bc_tol=1.e-14):
         """ar:121-189.  Stand-alone arteries get their own device network."""
         self.q0, self.theta = q0, theta
-        self.pn = _NodalFunction(self.dx, np.full(self.Nx + 1, self.param['p0']))
+        self._pn = None                  # pn = p0 everywhere (ar:161-162), materialised on first use
         if (self._dev is None and not self._in_network) or self._own:
             self._create_private_device()
 
@@ -127,6 +129,16 @@ class Artery(object):
         self._dev, self._k, self._b, self._own, self._in_network = dev, k, b, False, True
 
     # ---- state -------------------------------------------------------------------
+    @property
+    def pn(self):
+        if self._pn is None:
+            self._pn = _NodalFunction(self.dx, np.full(self.Nx + 1, self.param['p0']))
+        return self._pn
+
+    @pn.setter
+    def pn(self, value):
+        self._pn = value
+
     @property
     def Un(self):
         return _StateView(self, 0)
@@ -155,6 +167,7 @@ class Artery(object):
         RuntimeError on non-convergence like DOLFIN's NewtonSolver."""
         self._dev.artery_solve(self._k, self._b)
         if int(self._dev.get_flags()[self._b]) & _ffi.AF_FLAG_ARTERY_NOCONV:
+            self._dev.clear_flags()           # the bits are sticky; this failure has been reported
             raise RuntimeError("Newton solver did not converge for artery %d" % self.i)
 
     def update_solution(self):

@@ -41,6 +41,36 @@ class _JunctionX(np.ndarray):
             self._dev.set_junction_x(np.asarray(self)[None])
 
 
+class _Arteries(object):
+    """``an.arteries``: the reference's heap-indexed list of Artery objects (``None`` where the tree
+    has no vessel, an:87-93).  The facades carry no state of their own -- everything lives on the
+    device -- so they are built on first access: constructing a 255-vessel network does not pay for
+    255 Python objects it may never touch."""
+
+    def __init__(self, net):
+        self._net, self._made = net, {}
+
+    def __len__(self):
+        return self._net.N
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(self._net.N))]
+        if i < 0:
+            i += self._net.N
+        if not 0 <= i < self._net.N:
+            raise IndexError(i)
+        if not self._net._exists[i]:
+            return None
+        a = self._made.get(i)
+        if a is None:
+            a = self._made[i] = self._net._make_artery(i)
+        return a
+
+    def __iter__(self):
+        return (self[i] for i in range(self._net.N))
+
+
 class ArteryNetwork(object):
 
     def __init__(self, param, wk_scale=None, device=0, stream=None, _host_only=False):
@@ -87,29 +117,22 @@ class ArteryNetwork(object):
 
         self.check_geometry()
 
-        self.arteries = [None] * self.N
-        for i in range(self.N):
-            if self.nondim['Ru'][i] != 0:
-                self.arteries[i] = Artery(i, self.T, self.nondim)
-        self.arteries[0].root = True
-
+        # an:87-118 -- which vessels exist, root / parent / daughter / leaf classification
+        self._exists = np.asarray(self.nondim['Ru']) != 0
+        self.arteries = _Arteries(self)
         self.range_parent_arteries = [0]
         self.range_daughter_arteries = []
         self.range_leaf_arteries = []
         for i in range(1, self.N):
-            if self.arteries[i] is None:
+            if not self._exists[i]:
                 continue
             self.range_daughter_arteries.append(i)
             d1, d2 = self.daughter_arteries(i)
             if d1 is None and d2 is None:
-                self.arteries[i].leaf = True
                 self.range_leaf_arteries.append(i)
             else:
                 self.range_parent_arteries.append(i)
-
-        for j, i in enumerate(self.range_leaf_arteries):
-            for key in ('R1', 'R2', 'CT'):
-                self.arteries[i].param[key] = self.nondim[key][j]
+        self._leaf_slot = {i: j for j, i in enumerate(self.range_leaf_arteries)}
 
         self._dev = None
         self.define_geometry()
@@ -119,7 +142,7 @@ class ArteryNetwork(object):
     def daughter_arteries(self, i):
         out = []
         for k in (2 * i + 1, 2 * i + 2):
-            out.append(k if k <= self.N - 1 and self.arteries[k] is not None else None)
+            out.append(k if k <= self.N - 1 and self._exists[k] else None)
         return out[0], out[1]
 
     def parent_artery(self, i):
@@ -166,22 +189,47 @@ class ArteryNetwork(object):
         assert n1 == nc, "CT must have the same number of values as R1. {} != {}".format(nc, n1)
 
     # ---- set-up -------------------------------------------------------------------
+    def _make_artery(self, i):
+        """The facade of vessel ``i`` (an:87-93, 121-127 + Artery.define_geometry / define_solution)."""
+        a = Artery(i, self.T, self.nondim, root=(i == 0), leaf=(i in self._leaf_slot))
+        if a.leaf:
+            j = self._leaf_slot[i]
+            for key in ('R1', 'R2', 'CT'):
+                a.param[key] = self.nondim[key][j]
+        a._in_network = True
+        a.define_geometry(self.geo)
+        if getattr(self, '_q0', None) is not None:
+            a._attach(self._dev, self._compact[i])
+            a.define_solution(self._q0[i], self.sol['theta'])
+        return a
+
     def define_geometry(self):
-        """artery_network.py:244-255."""
-        for artery in self.arteries:
-            if artery is not None:
-                artery.define_geometry(self.geo)
+        """artery_network.py:244-255: per-vessel geometry (Artery.define_geometry, ar:67-118), for all
+        vessels at once; facades built so far are refreshed."""
+        nd = self.nondim
+        idx = np.flatnonzero(self._exists)
+        self._idx = idx
+        Ru, Rd, L = (np.asarray(nd[k], dtype=float)[idx] for k in ('Ru', 'Rd', 'L'))
+        is_leaf = np.isin(idx, self.range_leaf_arteries)
+        if 'R_term' in nd:
+            Rd = np.where(is_leaf & (Rd == 1), nd['R_term'], Rd)          # ar:108-109
+        self._geom = dict(Ru=Ru, Rd=Rd, L=L)
+        self._db = float(np.sqrt(nd['nu'] * self.T / 2 / np.pi))              # ar:100, the same for every vessel
+        for a in self.arteries._made.values():
+            a.define_geometry(self.geo)
 
     def define_solution(self):
         """artery_network.py:258-279: initial flows (root q_ins[0]; daughters
         split by inlet rest areas), then the device-resident state."""
-        theta = self.sol['theta']
-        existing = [a for a in self.arteries if a is not None]
-        self._compact = {a.i: k for k, a in enumerate(existing)}
+        idx = self._idx
+        self._compact = {int(i): k for k, i in enumerate(idx)}
+        g = self._geom
+        # Artery.A0(0) of every vessel: pi * (Ru * (Rd/Ru)**(0/L))**2, the facade's expressions (ar:110-112)
+        A0_in = dict(zip(idx.tolist(), (np.pi * np.power(g['Ru'] * np.power(g['Rd'] / g['Ru'], 0 / g['L']), 2)).tolist()))
         q0 = {0: self.q_ins[0]}
         for i in self.range_daughter_arteries:
-            a, s = self.arteries[i], self.arteries[self.sister_artery(i)]
-            q0[i] = a.A0(0) / (a.A0(0) + s.A0(0)) * q0[self.parent_artery(i)]
+            a0, s0 = A0_in[i], A0_in[self.sister_artery(i)]
+            q0[i] = a0 / (a0 + s0) * q0[self.parent_artery(i)]
         junctions = []
         for ip in self.range_parent_arteries:
             i1, i2 = self.daughter_arteries(ip)
@@ -190,30 +238,29 @@ class ArteryNetwork(object):
                                  "(artery_network.py:111-118)" % ip)
             junctions.append([self._compact[ip], self._compact[i1], self._compact[i2]])
         leaves = [self._compact[i] for i in self.range_leaf_arteries]
-        self._description = self.describe(existing, junctions, leaves, q0)
+        self._q0 = q0
+        self._description = self.describe(junctions, leaves, q0)
         if self._dev is not None:
             self._dev.close()
         self._dev = self._make_device(self._description)
-        for a in existing:
+        for a in self.arteries._made.values():
             a._attach(self._dev, self._compact[a.i])
-            a.define_solution(q0[a.i], theta)
+            a.define_solution(q0[a.i], self.sol['theta'])
         if self._dev is not None:
-            self.x = np.ones([len(self.range_parent_arteries), 18])
+            self.x = np.ones([len(self.range_parent_arteries), 18])       # an:279 (define_x replaces it, an:874)
 
-    def describe(self, existing, junctions, leaves, q0):
+    def describe(self, junctions, leaves, q0):
         """Flat, nondimensional description of the network: exactly the arrays
         af_desc takes (include/arteryfe_b200.h).  Also used by the ensemble
         driver, which stacks perturbed copies of it."""
-        nd = self.nondim
+        nd, g = self.nondim, self._geom
+        R1, R2, CT = (np.asarray(nd[k], dtype=float)[:len(leaves)] for k in ('R1', 'R2', 'CT'))
         return dict(
             Nx=self.geo['Nx'], Nt=self.geo['Nt'], theta=self.sol['theta'], dt=self.dt,
             junctions=np.array(junctions, dtype=np.int32).reshape(-1, 3), leaves=np.array(leaves, dtype=np.int32),
-            k1=nd['k1'], k2=nd['k2'], k3=nd['k3'], rho=nd['rho'], Re=nd['Re'], db=existing[0].db, p0=nd['p0'],
-            Ru=np.array([a._Ru for a in existing]), Rd=np.array([a._Rd for a in existing]),
-            L=np.array([a._L for a in existing]), q0=np.array([q0[a.i] for a in existing]),
-            R1=np.array([self.arteries[i].param['R1'] * self.wk_scale[0] for i in self.range_leaf_arteries]),
-            R2=np.array([self.arteries[i].param['R2'] * self.wk_scale[1] for i in self.range_leaf_arteries]),
-            CT=np.array([self.arteries[i].param['CT'] for i in self.range_leaf_arteries]),
+            k1=nd['k1'], k2=nd['k2'], k3=nd['k3'], rho=nd['rho'], Re=nd['Re'], db=self._db, p0=nd['p0'],
+            Ru=g['Ru'], Rd=g['Rd'], L=g['L'], q0=np.array([q0[int(i)] for i in self._idx]),
+            R1=R1 * self.wk_scale[0], R2=R2 * self.wk_scale[1], CT=CT,
             q_ins=self.q_ins)
 
     def _make_device(self, d):
@@ -278,10 +325,18 @@ class ArteryNetwork(object):
 
     def define_x(self):
         """artery_network.py:464-473."""
-        x = np.zeros((len(self.range_parent_arteries), 18))
-        for k, ip in enumerate(self.range_parent_arteries):
-            i1, i2 = self.daughter_arteries(ip)
-            x[k] = self.initial_x(self.arteries[ip], self.arteries[i1], self.arteries[i2])
+        d = self._description
+        jn = d['junctions']
+        if len(jn) == 0:
+            self.x = np.zeros((0, 18))
+            return
+        # initial_x for every junction at once: q0 x3 and A0(end) x3 per vessel (an:434-461)
+        q0 = d['q0'][jn]                                           # [nj, 3]
+        Ru, Rd = d['Ru'][jn], d['Rd'][jn]
+        frac = np.zeros_like(Ru)
+        frac[:, 0] = 1.0                                           # parent: x = L, daughters: x = 0
+        A_end = np.pi * np.power(Ru * np.power(Rd / Ru, frac), 2)  # Artery.A0 at x/L = frac, same expressions
+        x = np.concatenate([np.repeat(q0, 3, axis=1), np.repeat(A_end, 3, axis=1)], axis=1)
         self.x = x
 
     def problem_function(self, p, d1, d2, x):
@@ -303,7 +358,7 @@ class ArteryNetwork(object):
 
     def adjust_bifurcation_step(self, p, d1, d2, margin=0.05):
         """artery_network.py:713-737."""
-        dex = self._dev.junction_cfl_dex(self._junction_of(p)) * (1 + margin) / 1.05
+        dex = (1 + margin) * self.dt / self._dev.junction_cfl_min(self._junction_of(p))     # an:737, same order
         allx = self._dev.get_dex()
         for a in (p, d1, d2):
             allx[0, a._k] = dex
@@ -362,7 +417,8 @@ class ArteryNetwork(object):
         """The dump test ``n % (Nt/Nt_store) == 0`` of artery_network.py:926,
         float modulo included, for every n of a cycle."""
         Nt, Nt_store = self.geo['Nt'], self.sol['Nt_store']
-        return np.array([n % (Nt / Nt_store) == 0 for n in range(Nt)], dtype=np.uint8)
+        # numpy's float remainder is Python's for non-negative operands (both are C fmod)
+        return (np.arange(Nt) % (Nt / Nt_store) == 0).astype(np.uint8)
 
     def solve(self, write_output=True, n_steps=None):
         """artery_network.py:857-946.  The whole loop runs on the device; the
@@ -371,6 +427,7 @@ class ArteryNetwork(object):
         dict (``t``, ``flow``, ``area``, ``pressure``: [snapshot, artery, vertex]).
         ``n_steps`` (not in the reference) stops the loop early."""
         self.define_x()
+        self._dev.clear_flags()
         if write_output:
             self.dump_metadata()
         Nt, N_cycles = self.geo['Nt'], self.geo['N_cycles']
@@ -390,11 +447,17 @@ class ArteryNetwork(object):
         self._dev.stream_store_to_host()         # snapshots leave the device while the loop runs
         self._dev.step(0, total)
         snaps = self._dev.fetch_snapshots()      # streams the snapshots out while the loop is still running
-        self._dev.sync()
+        # a failed artery solve ends the loop at its step: the launches queued behind it return at once and
+        # af_net_step stops enqueuing (DOLFIN raises inside that step, artery.py:244)
+        bad = self._dev.failed_step()
         flags = int(self._dev.get_flags()[0])
-        if flags & _ffi.AF_FLAG_ARTERY_NOCONV:
-            raise RuntimeError("Newton solver did not converge in an artery solve "
-                               "(flags=0x%x; DOLFIN raises here, artery.py:244)" % flags)
+        self.flags = flags
+        if bad >= 0 or flags & _ffi.AF_FLAG_ARTERY_NOCONV:
+            self.failed_step = bad
+            raise RuntimeError("Newton solver did not converge in an artery solve at time step %d "
+                               "(cycle %d, n = %d; flags=0x%x%s; DOLFIN raises here, artery.py:244)"
+                               % (bad, bad // Nt, bad % Nt, flags,
+                                  ", non-finite residual" if flags & _ffi.AF_FLAG_NONFINITE else ""))
         # t is accumulated by repeated "t += dt" (artery_network.py:946)
         t_all = np.concatenate([[0.0], np.cumsum(np.full(N_cycles * Nt, self.dt))])
         res = {'t': t_all[snaps['step']], 'step': snaps['step']}

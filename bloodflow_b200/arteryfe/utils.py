@@ -76,10 +76,19 @@ def redimensionalise(rc, qc, rho, x, nature):
 def read_inlet(data_location, Nt):
     """utils.py:173-200: (T, q_ins) with q_ins the CSV linearly interpolated at
     ``linspace(0, T, Nt)`` -- spacing T/(Nt-1), not dt."""
-    table = np.genfromtxt(data_location, delimiter=',')
-    T = table[-1, 0]
-    q_ins = interp1d(table[:, 0], table[:, 1])(np.linspace(0, T, Nt))
-    return T, q_ins
+    key = (os.path.abspath(data_location), os.path.getmtime(data_location), int(Nt))
+    hit = _inlet_cache.get(key)
+    if hit is None:                      # parameter studies build many networks on the same inlet file
+        table = np.genfromtxt(data_location, delimiter=',')
+        T = table[-1, 0]
+        q_ins = interp1d(table[:, 0], table[:, 1])(np.linspace(0, T, Nt))
+        if len(_inlet_cache) > 16:
+            _inlet_cache.clear()
+        hit = _inlet_cache[key] = (T, q_ins)
+    return hit[0], hit[1].copy()
+
+
+_inlet_cache = {}
 
 
 def read_output(filename):

@@ -30,6 +30,8 @@
 
 using namespace af;
 
+#define AF_NO_FAIL 0xffffffffffffffffull
+
 // ---------------------------------------------------------------------------
 // device view
 // ---------------------------------------------------------------------------
@@ -62,6 +64,8 @@ struct NetDev {
   int* picard_its;
   unsigned long long* totals;  // [3]
   uint32_t* flags;             // [nb]
+  unsigned long long* fail_step;  // [1] first global step at which an artery Newton failed (AF_NO_FAIL: none)
+  int stop_on_fail;            // single networks: every later launch returns at once (DOLFIN raises, ar:244)
   // solver constants
   double newton_rtol, newton_atol;
   int newton_max_it, junction_k_max, picard_k_max;
@@ -309,7 +313,7 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
   nd.picard_its[b * nd.nl + l] = r.its;
   if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
   atomicAdd(&nd.totals[2], (unsigned long long)r.its);
-  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)AF_FLAG_PICARD_KMAX);
+  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)(r.cycle ? AF_FLAG_PICARD_CYCLE : AF_FLAG_PICARD_KMAX));
 }
 
 // one warp per leaf (single networks): lanes 0..2 take the three stencil points
@@ -353,7 +357,7 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   const double A0s = __shfl_sync(FULL, Ak, 2), q0s = __shfl_sync(FULL, qk, 2);
   const double qm1 = q1 - AF_DIV(dt, dex) * (F10 - F21) + dt / 2.0 * (S10 + S21);
   WkResult r;
-  r.A_out = 0.0; r.dex = dex; r.its = 0;
+  r.A_out = 0.0; r.dex = dex; r.its = 0; r.cycle = 0;
   if (lane != 0) return r;
   const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
   r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
@@ -362,7 +366,7 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   nd.picard_its[b * nd.nl + l] = r.its;
   if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
   atomicAdd(&nd.totals[2], (unsigned long long)r.its);
-  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)AF_FLAG_PICARD_KMAX);
+  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)(r.cycle ? AF_FLAG_PICARD_CYCLE : AF_FLAG_PICARD_KMAX));
   return r;
 }
 
@@ -403,6 +407,7 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl) {
     // only now may the artery kernel of THIS step start its prologue: it reads the
     // Un that the previous artery kernel has just finished writing
     cudaTriggerProgrammaticLaunchCompletion();
+    if (nd.stop_on_fail && *nd.fail_step != AF_NO_FAIL) return;     // an artery solve failed: the run is over
     if (is_junction)
       junction_task_warp(nd, cur, b, j, ia, ves, log_slot);
     else if (is_leaf)
@@ -617,7 +622,7 @@ __device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const doubl
 
 template <int T, bool FUSED>
 __global__ void __launch_bounds__(T, (T == 32 ? AF_T32_BLOCKS : (T <= 256 ? 512 / T : 1)))
-k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
+k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long gstep) {
   extern __shared__ double sm[];
   __shared__ double red[32];
   __shared__ double bcv[4];
@@ -633,6 +638,10 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
 
   // the next boundary kernel may be made resident early; it waits for this grid to finish
   cudaTriggerProgrammaticLaunchCompletion();
+  // A failed artery solve of an earlier step ends a single-network run (DOLFIN raises there,
+  // ar:244).  The previous artery kernel has completed before this one can start (the boundary
+  // kernel between them waits for it before it triggers), so its fail_step is visible here.
+  if (nd.stop_on_fail && *nd.fail_step != AF_NO_FAIL) return;
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
   const Vessel v = nd.ves[ba];
@@ -753,8 +762,10 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
       // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
       c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
       c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
-      if (c.root && inlet_index >= 0)
+      if (c.root && inlet_index >= 0) {
         c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
+        if (tid == 0) nd.bc[ba * 4 + 1] = c.gqin;      // arteries[0].q_in = q_in (an:777): the holder keeps it
+      }
     }
     cta_sync<T>();
     double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
@@ -841,7 +852,10 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot) {
     nd.art_its[ba] = it;
     if (log_slot >= 0) nd.log_art[(size_t)log_slot * nd.nb * nd.na + ba] = it;
     atomicAdd(&nd.totals[0], (unsigned long long)it);
-    if (fl) atomicOr(&nd.flags[b], fl);
+    if (fl) {
+      atomicOr(&nd.flags[b], fl);
+      if (fl & AF_FLAG_ARTERY_NOCONV) atomicMin(nd.fail_step, (unsigned long long)(gstep >= 0 ? gstep : 0));
+    }
   }
 }
 
@@ -877,6 +891,56 @@ __global__ void k_dump_outlet(NetDev nd, int cur, double* out) {
   int b = t / nd.nl, l = t % nd.nl;
   int ba = b * nd.na + nd.leaf_art[l];
   out[t] = outlet_pressure(nd.ves[ba], nd.A[cur][(size_t)ba * nd.S + nd.Nx]);
+}
+
+// ---------------------------------------------------------------------------
+// ensemble statistics: moments of the stored leaf-outlet pressures over the members
+// ("statistics kernel + one collective")
+// op [n_snap][nb][nl] -> part [P][5][n_snap*nl] (count, sum, sum of squares, min, max), P = gridDim.y
+// member slices; k_moments_fold adds the P partials in index order (deterministic).
+// ---------------------------------------------------------------------------
+__global__ void k_outlet_moments(const double* op, int nb, int nl, int n_out, double* part) {
+  extern __shared__ double sh[];                 // [4][blockDim.x]
+  const int s = blockIdx.x, P = gridDim.y, pi = blockIdx.y;
+  const int B = blockDim.x;                      // a multiple of nl: thread t always sees leaf t % nl
+  const int m0 = (int)((long long)nb * pi / P), m1 = (int)((long long)nb * (pi + 1) / P);
+  const double* src = op + ((size_t)s * nb + m0) * nl;
+  const size_t cnt = (size_t)(m1 - m0) * nl;
+  double sum = 0.0, ssq = 0.0, lo = 1.0e300, hi = -1.0e300;
+  for (size_t i = threadIdx.x; i < cnt; i += B) {
+    const double v = src[i];
+    sum += v; ssq = fma(v, v, ssq);
+    lo = v < lo ? v : lo; hi = v > hi ? v : hi;
+  }
+  sh[threadIdx.x] = sum; sh[B + threadIdx.x] = ssq; sh[2 * B + threadIdx.x] = lo; sh[3 * B + threadIdx.x] = hi;
+  __syncthreads();
+  if (threadIdx.x < nl) {
+    const int l = threadIdx.x;
+    sum = 0.0; ssq = 0.0; lo = 1.0e300; hi = -1.0e300;
+    for (int t = l; t < B; t += nl) {            // fixed order
+      sum += sh[t]; ssq += sh[B + t];
+      lo = sh[2 * B + t] < lo ? sh[2 * B + t] : lo; hi = sh[3 * B + t] > hi ? sh[3 * B + t] : hi;
+    }
+    double* o = part + (size_t)pi * 5 * n_out + (size_t)s * nl + l;
+    o[0] = (double)(m1 - m0); o[n_out] = sum; o[2 * (size_t)n_out] = ssq; o[3 * (size_t)n_out] = lo; o[4 * (size_t)n_out] = hi;
+  }
+}
+
+// parts [P][5][n] -> out [5][n]; finalize = 0: (count, sum, ssq, min, max), 1: (count, mean, variance, min, max)
+__global__ void k_moments_fold(const double* parts, int P, int n, int finalize, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double c = 0.0, sum = 0.0, ssq = 0.0, lo = 1.0e300, hi = -1.0e300;
+  for (int p = 0; p < P; ++p) {
+    const double* q = parts + (size_t)p * 5 * n + i;
+    c += q[0]; sum += q[n]; ssq += q[2 * (size_t)n];
+    lo = q[3 * (size_t)n] < lo ? q[3 * (size_t)n] : lo; hi = q[4 * (size_t)n] > hi ? q[4 * (size_t)n] : hi;
+  }
+  if (finalize) {
+    const double mean = sum / c, var = ssq / c - mean * mean;
+    sum = mean; ssq = var > 0.0 ? var : 0.0;
+  }
+  out[i] = c; out[n + i] = sum; out[2 * (size_t)n + i] = ssq; out[3 * (size_t)n + i] = lo; out[4 * (size_t)n + i] = hi;
 }
 
 // state <-> dense host layout
@@ -954,6 +1018,7 @@ __global__ void k_junction_debug(NetDev nd, int cur, int b, int j, int mode, con
       M = m < M ? m : M;
     }
     out[0] = (1.0 + nd.cfl_margin) * nd.dt / M;
+    out[1] = M;
     return;
   }
   JunctionCtx c;
@@ -986,6 +1051,7 @@ __global__ void k_junction_debug(NetDev nd, int cur, int b, int j, int mode, con
     for (int i = 0; i < 18; ++i) out[i] = x[i];
     out[18] = (double)solves;
     out[19] = (double)fl;
+    if (fl) atomicOr(&nd.flags[b], fl);       // e.g. AF_FLAG_SINGULAR: the reference prints 'Singular' (an:704)
   }
 }
 
@@ -1022,14 +1088,14 @@ static int fail(int code, const std::string& msg) {
 // to the next request of exactly the same size.  Parameter sweeps and ensembles create
 // and destroy same-shaped networks in a loop; cudaMalloc / cudaFree / cudaHostAlloc of
 // the state and the snapshot store cost as much as ~1000 time steps of the order-8 tree
-// (scripts/e2e_breakdown.py).  AF_CACHE_MB caps the cached device bytes (default 4096,
+// (scripts/e2e_breakdown.py).  AF_CACHE_MB caps the cached device bytes (default 1024,
 // 0 disables both caches); af_release_cached_memory() empties them.
 struct BlockCache {
   std::mutex mu;
   std::multimap<std::pair<int, size_t>, void*> dev;    // (device, bytes) -> block
   std::multimap<size_t, void*> host;                   // pinned
   size_t dev_bytes = 0, host_bytes = 0;
-  size_t dev_cap = (size_t)4096 << 20, host_cap = (size_t)512 << 20;
+  size_t dev_cap = (size_t)1024 << 20, host_cap = (size_t)256 << 20;
   BlockCache() {
     if (const char* env = getenv("AF_CACHE_MB")) {
       long long mb = atoll(env);
@@ -1120,6 +1186,16 @@ struct af_net {
   int n_sub = 1;
   cudaStream_t sub[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
+  // failure polling (single networks): every kPoll steps the device's fail_step is copied to a pinned
+  // word; once it shows a failed artery solve af_net_step stops enqueuing (the launches already queued
+  // return at once, see k_artery)
+  static const int kPoll = 64;
+  unsigned long long* fail_h = nullptr;   // pinned
+  cudaEvent_t fail_ev = nullptr;
+  bool fail_poll_pending = false;
+  bool failed = false;
+  double* moments = nullptr;      // [5][n_snap*nl] outlet-pressure moments over the members (+ partials)
+  size_t moments_cap = 0;
   std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
   int n_pending = 0;
 
@@ -1128,10 +1204,13 @@ struct af_net {
     const size_t bytes = (((n ? n : 1) * sizeof(Tp)) + 511) & ~(size_t)511;
     void* q = cache().take_dev(device, bytes);
     if (q) {
-      // a recycled block holds the previous owner's data; small ones are cleared like the
-      // zero pages a fresh cudaMalloc hands out in practice, the bulk buffers (state, store)
-      // are always written before they are read
-      if (bytes <= ((size_t)1 << 20)) cudaMemsetAsync(q, 0, bytes, stream);
+      // a recycled block holds the previous owner's data: clear it (a memset at HBM speed is
+      // far cheaper than the cudaMalloc it replaces)
+      cudaError_t e = cudaMemsetAsync(q, 0, bytes, stream);
+      if (e != cudaSuccess) {
+        cudaFree(q);
+        return fail(AF_ECUDA, std::string("cudaMemsetAsync of a recycled block: ") + cudaGetErrorString(e));
+      }
     } else {
       cudaError_t e = cudaMalloc(&q, bytes);
       if (e == cudaErrorMemoryAllocation) {           // give the cached blocks back and retry once
@@ -1220,9 +1299,11 @@ extern "C" void af_desc_defaults(af_desc* d) {
 
 template <int T>
 static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot, bool fused,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, long long gstep) {
+  NetDev nd = n->nd;
+  if (gstep < 0) nd.stop_on_fail = 0;      // single-phase entry points always run
   if (fused && T >= 64) {
-    k_artery<T, (T >= 64)><<<count, T, n->artery_smem, stream>>>(n->nd, n->cur, ba0, inlet_index, log_slot);
+    k_artery<T, (T >= 64)><<<count, T, n->artery_smem, stream>>>(nd, n->cur, ba0, inlet_index, log_slot, gstep);
     return cudaGetLastError();
   }
   // programmatic stream serialisation: may start while the preceding kernel of the
@@ -1237,7 +1318,7 @@ static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_
   attr[0].val.programmaticStreamSerializationAllowed = n->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_artery<T, false>, n->nd, n->cur, ba0, inlet_index, log_slot);
+  return cudaLaunchKernelEx(&cfg, k_artery<T, false>, nd, n->cur, ba0, inlet_index, log_slot, gstep);
 }
 
 template <int T>
@@ -1251,18 +1332,21 @@ static cudaError_t prepare_artery(af_net* n) {
 }
 
 static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_index, int log_slot,
-                              bool fused = false, cudaStream_t stream = nullptr) {
+                              bool fused = false, cudaStream_t stream = nullptr, long long gstep = -1) {
   if (!stream) stream = n->stream;
   switch (n->artery_threads) {
-    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot, fused, stream);
-    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot, fused, stream);
-    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot, fused, stream);
-    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot, fused, stream);
-    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused, stream);
+    case 32: return launch_artery<32>(n, ba0, count, inlet_index, log_slot, fused, stream, gstep);
+    case 64: return launch_artery<64>(n, ba0, count, inlet_index, log_slot, fused, stream, gstep);
+    case 128: return launch_artery<128>(n, ba0, count, inlet_index, log_slot, fused, stream, gstep);
+    case 256: return launch_artery<256>(n, ba0, count, inlet_index, log_slot, fused, stream, gstep);
+    default: return launch_artery<512>(n, ba0, count, inlet_index, log_slot, fused, stream, gstep);
   }
 }
 
-static cudaError_t run_boundary(const af_net* n, int log_slot, int b0 = 0, int nbl = -1, cudaStream_t stream = nullptr) {
+static cudaError_t run_boundary(const af_net* n, int log_slot, int b0 = 0, int nbl = -1, cudaStream_t stream = nullptr,
+                                bool in_loop = false) {
+  NetDev nd = n->nd;
+  if (!in_loop) nd.stop_on_fail = 0;
   if (nbl < 0) nbl = n->nd.nb;
   if (!stream) stream = n->stream;
   long long tasks = (long long)nbl * (n->nd.nj + n->nd.nl);
@@ -1280,8 +1364,8 @@ static cudaError_t run_boundary(const af_net* n, int log_slot, int b0 = 0, int n
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (n->boundary_lanes == 32)
-    return cudaLaunchKernelEx(&cfg, k_boundary<true>, n->nd, n->cur, log_slot, b0, nbl);
-  return cudaLaunchKernelEx(&cfg, k_boundary<false>, n->nd, n->cur, log_slot, b0, nbl);
+    return cudaLaunchKernelEx(&cfg, k_boundary<true>, nd, n->cur, log_slot, b0, nbl);
+  return cudaLaunchKernelEx(&cfg, k_boundary<false>, nd, n->cur, log_slot, b0, nbl);
 }
 
 extern "C" int af_net_create(const af_desc* d, af_net** out) {
@@ -1406,12 +1490,21 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   AF_TRY(n->dalloc(&nd.picard_its, (size_t)nd.nb * nd.nl));
   AF_TRY(n->dalloc(&nd.totals, 3));
   AF_TRY(n->dalloc(&nd.flags, nd.nb));
+  AF_TRY(n->dalloc(&nd.fail_step, 1));
   AF_TRY(n->dalloc(&n->scratch, 4096));
   cudaMemsetAsync(nd.art_its, 0, nba * sizeof(int), n->stream);
   cudaMemsetAsync(nd.j_solves, 0, (size_t)nd.nb * nd.nj * sizeof(int) + 0, n->stream);
   cudaMemsetAsync(nd.picard_its, 0, (size_t)nd.nb * nd.nl * sizeof(int) + 0, n->stream);
   cudaMemsetAsync(nd.totals, 0, 3 * sizeof(unsigned long long), n->stream);
   cudaMemsetAsync(nd.flags, 0, nd.nb * sizeof(uint32_t), n->stream);
+  cudaMemsetAsync(nd.fail_step, 0xff, sizeof(unsigned long long), n->stream);      // AF_NO_FAIL
+  nd.stop_on_fail = (nd.nb == 1) ? 1 : 0;      // ensemble members are independent: a failed one is only flagged
+  if (nd.stop_on_fail) {
+    cudaError_t ef = cudaHostAlloc((void**)&n->fail_h, sizeof(unsigned long long), cudaHostAllocDefault);
+    if (ef == cudaSuccess) ef = cudaEventCreateWithFlags(&n->fail_ev, cudaEventDisableTiming);
+    if (ef != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("failure polling: ") + cudaGetErrorString(ef)); }
+    *n->fail_h = AF_NO_FAIL;
+  }
 
   n->pending.assign(nba, 0);
   // launch configuration
@@ -1484,6 +1577,8 @@ extern "C" void af_net_destroy(af_net* n) {
     if (n->ev_join[k]) cudaEventDestroy(n->ev_join[k]);
   }
   if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+  if (n->fail_ev) cudaEventDestroy(n->fail_ev);
+  if (n->fail_h) cudaFreeHost(n->fail_h);
   for (auto& blk : n->allocs) af_net::release_block(n->device, blk.first, blk.second);
   for (cudaEvent_t ev : n->snap_event) cudaEventDestroy(ev);
   for (int k = 0; k < af_net::kRing; ++k) if (n->ring_done[k]) cudaEventDestroy(n->ring_done[k]);
@@ -1630,6 +1725,18 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
   for (int64_t g = n_first; g < n_first + n_steps; ++g) {
     int step = (int)(g % Nt);
     int64_t cycle = g / Nt;
+    if (n->fail_h && (g % af_net::kPoll) == 0) {
+      if (n->fail_poll_pending && cudaEventQuery(n->fail_ev) == cudaSuccess) {
+        n->fail_poll_pending = false;
+        if (*n->fail_h != AF_NO_FAIL) n->failed = true;
+      }
+      if (n->failed) break;                  // what is already enqueued drains without doing anything
+      if (!n->fail_poll_pending) {
+        AF_CUDA(cudaMemcpyAsync(n->fail_h, n->nd.fail_step, sizeof(unsigned long long), cudaMemcpyDeviceToHost, n->stream));
+        AF_CUDA(cudaEventRecord(n->fail_ev, n->stream));
+        n->fail_poll_pending = true;
+      }
+    }
     if (n->max_snap && cycle >= n->first_cycle && n->mask[step] && n->n_snap < n->max_snap) {
       // the dump kernels read every member: gather the shares, dump on the handle's stream, release them
       if (split && (rc = join_subs(n))) return rc;
@@ -1644,17 +1751,17 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     int log_slot = (n->log_n < n->log_cap) ? n->log_n++ : -1;
     int inlet = (step + 1) % Nt;                       // an:916
     if (n->fused) {
-      AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot, true));
+      AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot, true, nullptr, g));
       std::swap(n->nd.jx, n->nd.jx_next);
     } else if (split) {
       for (int k = 0; k < n->n_sub; ++k) {
         const int b0 = (int)((long long)n->nd.nb * k / n->n_sub), b1 = (int)((long long)n->nd.nb * (k + 1) / n->n_sub);
-        AF_CUDA(run_boundary(n, log_slot, b0, b1 - b0, n->sub[k]));
-        AF_CUDA(run_artery(n, b0 * n->nd.na, (b1 - b0) * n->nd.na, inlet, log_slot, false, n->sub[k]));
+        AF_CUDA(run_boundary(n, log_slot, b0, b1 - b0, n->sub[k], true));
+        AF_CUDA(run_artery(n, b0 * n->nd.na, (b1 - b0) * n->nd.na, inlet, log_slot, false, n->sub[k], g));
       }
     } else {
-      AF_CUDA(run_boundary(n, log_slot));
-      AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot));
+      AF_CUDA(run_boundary(n, log_slot, 0, -1, nullptr, true));
+      AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot, false, nullptr, g));
     }
     n->cur ^= 1;
   }
@@ -1815,14 +1922,53 @@ extern "C" int af_net_outlet_pressure_d(af_net* n, double** ptr_d) {
   return AF_OK;
 }
 
+extern "C" int af_net_outlet_moments_d(af_net* n, double** moments_d, int32_t* n_snapshots) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!moments_d) return fail(AF_EINVAL, "null argument");
+  if (!n->s_outlet) return fail(AF_ESTATE, "outlet pressure not stored");
+  const NetDev& nd = n->nd;
+  if (nd.nl < 1 || nd.nl > 1024) return fail(AF_EINVAL, "1..1024 leaves supported");
+  const int ns = n->n_snap, n_out = ns * nd.nl;
+  if (n_snapshots) *n_snapshots = ns;
+  if (ns == 0) { *moments_d = nullptr; return AF_OK; }
+  int P = nd.nb / 1024;                          // member slices per snapshot (>= 1024 members each)
+  P = P < 1 ? 1 : (P > 32 ? 32 : P);
+  const size_t need = (size_t)(P + 1) * 5 * n_out;
+  if (need > n->moments_cap) {
+    AF_CUDA(cudaStreamSynchronize(n->stream));
+    n->dfree(&n->moments);
+    n->moments_cap = 0;
+    if ((rc = n->dalloc(&n->moments, need))) return rc;
+    n->moments_cap = need;
+  }
+  const int B = nd.nl * (256 / nd.nl > 0 ? 256 / nd.nl : 1);
+  double* parts = n->moments + (size_t)5 * n_out;
+  k_outlet_moments<<<dim3(ns, P), B, 4 * B * sizeof(double), n->stream>>>(n->s_outlet, nd.nb, nd.nl, n_out, parts);
+  AF_CUDA(cudaGetLastError());
+  k_moments_fold<<<(n_out + 127) / 128, 128, 0, n->stream>>>(parts, P, n_out, 0, n->moments);
+  AF_CUDA(cudaGetLastError());
+  *moments_d = n->moments;
+  return AF_OK;
+}
+
+extern "C" int af_moments_combine_d(int32_t device, void* stream, const double* parts_d, int32_t n_parts, int32_t n,
+                                    double* out_d) {
+  if (!parts_d || !out_d || n_parts < 1 || n < 1) return fail(AF_EINVAL, "bad argument");
+  AF_CUDA(cudaSetDevice(device));
+  k_moments_fold<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(parts_d, n_parts, n, 1, out_d);
+  AF_CUDA(cudaGetLastError());
+  return AF_OK;
+}
+
 // dense <-> padded copies go through a temporary device buffer
 static int with_dense(af_net* n, double* hA, double* hq, const double* cA, const double* cq, bool to_host) {
   const NetDev& nd = n->nd;
   size_t cnt = (size_t)nd.nb * nd.na * nd.np;
-  double *dA = nullptr, *dq = nullptr;
-  AF_CUDA(cudaMalloc(&dA, cnt * sizeof(double)));
-  cudaError_t e = cudaMalloc(&dq, cnt * sizeof(double));
-  if (e != cudaSuccess) { cudaFree(dA); return fail(AF_ENOMEM, cudaGetErrorString(e)); }
+  double *dA = nullptr, *dq = nullptr;       // from the handle's block cache, returned below
+  int rc = n->dalloc(&dA, cnt);
+  if (rc) return rc;
+  if ((rc = n->dalloc(&dq, cnt))) { n->dfree(&dA); return rc; }
   if (to_host) {
     k_pack<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, dA, dq);
     cudaMemcpyAsync(hA, dA, cnt * sizeof(double), cudaMemcpyDeviceToHost, n->stream);
@@ -1833,8 +1979,8 @@ static int with_dense(af_net* n, double* hA, double* hq, const double* cA, const
     k_unpack<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, dA, dq);
     // the Newton initial guess U is Un (ar:158), nothing else to reset
   }
-  e = cudaStreamSynchronize(n->stream);
-  cudaFree(dA); cudaFree(dq);
+  cudaError_t e = cudaStreamSynchronize(n->stream);
+  n->dfree(&dA); n->dfree(&dq);
   if (e != cudaSuccess) return fail(AF_ECUDA, cudaGetErrorString(e));
   return AF_OK;
 }
@@ -1862,11 +2008,11 @@ extern "C" int af_net_get_pressure(af_net* n, double* p) {
   const NetDev& nd = n->nd;
   size_t cnt = (size_t)nd.nb * nd.na * nd.np;
   double* dp = nullptr;
-  AF_CUDA(cudaMalloc(&dp, cnt * sizeof(double)));
+  if ((rc = n->dalloc(&dp, cnt))) return rc;
   k_dump<<<nd.nb * nd.na, 128, 0, n->stream>>>(nd, n->cur, AF_STORE_PRESSURE, nullptr, nullptr, dp);
   cudaMemcpyAsync(p, dp, cnt * sizeof(double), cudaMemcpyDeviceToHost, n->stream);
   cudaError_t e = cudaStreamSynchronize(n->stream);
-  cudaFree(dp);
+  n->dfree(&dp);
   if (e != cudaSuccess) return fail(AF_ECUDA, cudaGetErrorString(e));
   return AF_OK;
 }
@@ -1926,6 +2072,28 @@ extern "C" int af_net_get_totals(af_net* n, int64_t totals[3]) {
 extern "C" int af_net_get_flags(af_net* n, uint32_t* flags) {
   int rc = check(n);
   return rc ? rc : d2h(n, flags, n->nd.flags, (size_t)n->nd.nb);
+}
+
+extern "C" int af_net_clear_flags(af_net* n) {
+  int rc = check(n);
+  if (rc) return rc;
+  AF_CUDA(cudaStreamSynchronize(n->stream));
+  AF_CUDA(cudaMemsetAsync(n->nd.flags, 0, n->nd.nb * sizeof(uint32_t), n->stream));
+  AF_CUDA(cudaMemsetAsync(n->nd.fail_step, 0xff, sizeof(unsigned long long), n->stream));
+  if (n->fail_h) *n->fail_h = AF_NO_FAIL;
+  n->failed = false;
+  n->fail_poll_pending = false;
+  return AF_OK;
+}
+
+extern "C" int af_net_failed_step(af_net* n, int64_t* step) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!step) return fail(AF_EINVAL, "null argument");
+  unsigned long long v = AF_NO_FAIL;
+  if ((rc = d2h(n, &v, n->nd.fail_step, 1))) return rc;
+  *step = v == AF_NO_FAIL ? -1 : (int64_t)v;
+  return AF_OK;
 }
 
 extern "C" int af_net_set_counter_log(af_net* n, int32_t capacity) {
@@ -2060,6 +2228,15 @@ static int junction_call(af_net* n, int network, int junction, int mode, const d
 extern "C" int af_junction_cfl_dex(af_net* n, int32_t network, int32_t junction, double* dex) {
   if (!dex) return fail(AF_EINVAL, "null argument");
   return junction_call(n, network, junction, 0, nullptr, nullptr, 0, 0.0, dex, 1);
+}
+
+extern "C" int af_junction_cfl_min(af_net* n, int32_t network, int32_t junction, double* M) {
+  if (!M) return fail(AF_EINVAL, "null argument");
+  double buf[2];
+  int rc = junction_call(n, network, junction, 0, nullptr, nullptr, 0, 0.0, buf, 2);
+  if (rc) return rc;
+  *M = buf[1];
+  return AF_OK;
 }
 
 extern "C" int af_junction_eval(af_net* n, int32_t network, int32_t junction, const double dex[3], const double* x,

@@ -79,6 +79,7 @@ constexpr double kW0 = 5.0 / 18.0, kW1 = 8.0 / 18.0, kW2 = 5.0 / 18.0;
 #define AF_FLAG_PICARD_KMAX 4u
 #define AF_FLAG_NONFINITE 8u
 #define AF_FLAG_SINGULAR 16u
+#define AF_FLAG_PICARD_CYCLE 32u
 #endif
 namespace af {
 
@@ -179,6 +180,7 @@ AF_HD double outlet_pressure(const Vessel& v, double A) {   // ar:285-301
 struct WkResult {
   double A_out, dex;
   int its;
+  int cycle;     // 1: the iteration fell into a round-off limit cycle and was cut short exactly
 };
 
 // The Picard iteration of an:405-422 given the outlet state (A0s, q0s) = Un(L),
@@ -186,6 +188,7 @@ struct WkResult {
 AF_HD WkResult windkessel_picard(const Vessel& v, double dt, double dex, double A0s, double q0s, double qm1,
                                  double R1, double R2, double CT, int k_max, double tol) {
   WkResult r;
+  r.cycle = 0;
   double pn = outlet_pressure(v, A0s);
   // Fixed-point map of an:411-420,
   //   qm0 = q + (p-pn)/R1 + dt/(R1 R2 C) pn - dt (R1+R2)/(R1 R2 C) q,
@@ -224,6 +227,7 @@ AF_HD WkResult windkessel_picard(const Vessel& v, double dt, double dex, double 
         Am0 = back == 0 ? Am0 : (back == 1 ? Am1 : Am2);
       }
       k = k_max;
+      r.cycle = 1;
       break;
     }
   }

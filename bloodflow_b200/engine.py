@@ -83,6 +83,22 @@ class DeviceNetwork(object):
     def sync(self):
         check(lib.af_net_sync(self._h))
 
+    def failed_step(self):
+        """Global step at which an artery Newton solve first failed, or -1 (waits for the stream)."""
+        s = ctypes.c_int64(-1)
+        check(lib.af_net_failed_step(self._h, ctypes.byref(s)))
+        return s.value
+
+    def clear_flags(self):
+        check(lib.af_net_clear_flags(self._h))
+
+    def outlet_moments_device(self):
+        """(device pointer, n_snapshots) of the packed moments [5][n_snapshots*n_leaves] of the stored
+        outlet pressures over this handle's members (count, sum, sum of squares, min, max)."""
+        p, n = ctypes.c_void_p(), ctypes.c_int32(0)
+        check(lib.af_net_outlet_moments_d(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
     def set_store(self, step_mask, first_cycle, max_snapshots, fields):
         mask = np.ascontiguousarray(step_mask, dtype=np.uint8)
         assert mask.shape == (self.Nt,)
@@ -266,6 +282,11 @@ class DeviceNetwork(object):
         d = ctypes.c_double(0)
         check(lib.af_junction_cfl_dex(self._h, int(network), int(junction), ctypes.byref(d)))
         return d.value
+
+    def junction_cfl_min(self, junction, network=0):
+        m = ctypes.c_double(0)
+        check(lib.af_junction_cfl_min(self._h, int(network), int(junction), ctypes.byref(m)))
+        return m.value
 
     def junction_eval(self, junction, dex3, x, network=0):
         dex3, x = f64(np.broadcast_to(dex3, (3,))), f64(x)

@@ -22,41 +22,7 @@ import numpy as np
 
 from . import _ffi
 from .engine import DeviceNetwork
-from .synthetic import leaf_radius
-
-SEED = 20260000
-
-
-def member_factors(i, n_leaves, seed=SEED):
-    rng = np.random.Generator(np.random.PCG64(seed + int(i)))
-    s = rng.uniform(0.9, 1.1)
-    r = rng.uniform(0.9, 1.1)
-    return s, r, rng.uniform(0.8, 1.2, n_leaves), rng.uniform(0.8, 1.2, n_leaves), rng.uniform(0.8, 1.2, n_leaves)
-
-
-def perturb_param(param, i, seed=SEED):
-    """The member-``i`` version of a ParamParser-like description (a tree built
-    from ``alpha``): what a user would feed to ArteryNetwork for that member."""
-    import copy
-    p = copy.deepcopy(param)
-    n_l = len(np.atleast_1d(p.param['R1']))
-    s, r, f1, f2, fc = member_factors(i, n_l, seed)
-    p.param['k1'] = p.param['k1'] * s
-    p.param['k3'] = p.param['k3'] * s
-    p.param['Ru'] = np.array(p.param['Ru'], dtype=float)
-    p.param['Rd'] = np.array(p.param['Rd'], dtype=float)
-    nominal_leaf = leaf_radius(p.param['Ru'][0], p.param['alpha'], p.param['order']) if 'alpha' in p.param else None
-    untapered_leaves = nominal_leaf is not None and p.param['R_term'] == nominal_leaf
-    p.param['Ru'][0] *= r
-    p.param['Rd'][0] *= r
-    # leaves that are untapered in the nominal tree (R_term == leaf Ru bitwise, SURVEY F9) stay so
-    p.param['R_term'] = (leaf_radius(p.param['Ru'][0], p.param['alpha'], p.param['order']) if untapered_leaves
-                         else p.param['R_term'] * r)
-    p.param['R1'] = np.atleast_1d(p.param['R1']) * f1
-    p.param['R2'] = np.atleast_1d(p.param['R2']) * f2
-    p.param['CT'] = np.atleast_1d(p.param['CT']) * fc
-    return p
-
+from .synthetic import SEED, leaf_radius, member_factors, perturb_param     # noqa: F401  (re-exported)
 
 def stacked_description(param, indices, seed=SEED, wk_scale=None):
     """Batched description of the members ``indices`` without building every
@@ -79,9 +45,8 @@ def stacked_description(param, indices, seed=SEED, wk_scale=None):
     R1, R2, CT = np.empty((nb, nl)), np.empty((nb, nl)), np.empty((nb, nl))
     # nominal lengths are L*Ru (- 0.01/rc for second daughters): separate the two parts
     short = np.zeros(na)
-    existing = [a for a in nominal.arteries if a is not None]
-    for k, a in enumerate(existing):
-        if a.i > 0 and a.i % 2 == 0:
+    for k, i in enumerate(nominal._idx):
+        if i > 0 and i % 2 == 0:
             short[k] = 0.01 / rc
     for m, i in enumerate(indices):
         s, r, f1, f2, fc = member_factors(i, nl, seed)
@@ -116,44 +81,72 @@ class EnsembleNetwork(object):
         self.dev.set_store(mask, n_cycles - n_cycles_store, max(1, int(mask.sum()) * n_cycles_store),
                            _ffi.AF_STORE_OUTLET_PRESSURE)
 
-    def solve(self, n_cycles=None, n_cycles_store=1):
-        """Returns the stored outlet pressures [snapshot, member, leaf]."""
+    def run(self, n_cycles=None, n_cycles_store=1):
+        """Enqueue the whole run; the stored outlet pressures stay on the device
+        (``device_moments`` / ``dev.fetch_snapshots``)."""
         n_cycles = self.geo['N_cycles'] if n_cycles is None else n_cycles
         self.configure_store(n_cycles, n_cycles_store)
         self.dev.step(0, n_cycles * self.geo['Nt'])
+
+    def solve(self, n_cycles=None, n_cycles_store=1):
+        """Returns the stored outlet pressures [snapshot, member, leaf]."""
+        self.run(n_cycles, n_cycles_store)
         self.dev.sync()
         return self.dev.fetch_snapshots()['outlet_pressure']
+
+    def flagged_members(self, mask=_ffi.AF_FLAG_ARTERY_NOCONV | _ffi.AF_FLAG_NONFINITE):
+        """Number of members whose status word has one of the ``mask`` bits."""
+        return int(np.count_nonzero(self.dev.get_flags() & np.uint32(mask)))
 
     def flags(self):
         return self.dev.get_flags()
 
 
 # ---- ensemble statistics -------------------------------------------------------------
-def local_moments(op):
-    """op: torch tensor [snapshot, member, leaf] (any device).  Returns the
-    additive / extremal moments over the local members:
-    (count, sum, sum of squares, min, max), each [snapshot, leaf]."""
+# Packed moments: a [5, n] tensor, rows = count, sum, sum of squares, min, max over members;
+# n = n_snapshots * n_leaves.  On the GPU the reduction over the members and the combination of the
+# ranks' buffers are kernels of the library (af_net_outlet_moments_d / af_moments_combine_d) and the
+# ranks exchange their packed buffers with ONE collective (all_gather).  The torch expressions below
+# do the same on CPU tensors; they exist for the gloo tests of the host logic only.
+def device_moments(dev, device):
+    """Packed moments [5, n_snapshots, n_leaves] of the members of ``dev`` (a DeviceNetwork), computed
+    on the device by the library; a zero-copy torch view of the library's buffer."""
+    ptr, n_snap = dev.outlet_moments_device()
+    return device_tensor(ptr, (5, n_snap, dev.nl), device)
+
+
+def host_moments(op):
+    """The same packed moments from a CPU tensor op [snapshot, member, leaf] (tests)."""
     import torch
     n = torch.full(op.shape[::2], float(op.shape[1]), dtype=op.dtype, device=op.device)
-    return [n, op.sum(dim=1), (op * op).sum(dim=1), op.min(dim=1).values, op.max(dim=1).values]
+    return torch.stack([n, op.sum(dim=1), (op * op).sum(dim=1), op.min(dim=1).values, op.max(dim=1).values])
 
 
-def reduce_moments(moments, group=None):
-    """All-reduce the moments over the ranks (NCCL for CUDA tensors, gloo for
-    CPU tensors): SUM for count / sum / sum of squares, MIN, MAX."""
+def combine_moments(packed, group=None):
+    """ONE collective: all-gather the ranks' packed moments (NCCL for CUDA tensors, gloo for CPU
+    tensors), then fold them.  Returns {count, mean, var, min, max}, each shaped like packed[0]."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        ops = (dist.ReduceOp.SUM, dist.ReduceOp.SUM, dist.ReduceOp.SUM, dist.ReduceOp.MIN, dist.ReduceOp.MAX)
-        for t, op in zip(moments, ops):
-            dist.all_reduce(t, op=op, group=group)
-    return moments
-
-
-def finalize(moments):
-    n, s, ss, lo, hi = moments
-    mean = s / n
-    var = (ss / n - mean * mean).clamp_min(0.0)
-    return {"count": n, "mean": mean, "var": var, "min": lo, "max": hi}
+    packed = packed.contiguous()
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world > 1:
+        flat = torch.empty(world * packed.numel(), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(flat, packed.reshape(-1), group=group)
+        parts = flat.view((world,) + tuple(packed.shape))
+    else:
+        parts = packed[None]
+    n = packed[0].numel()
+    if packed.is_cuda:
+        out = torch.empty_like(packed)
+        stream = torch.cuda.current_stream(packed.device).cuda_stream
+        _ffi.check(_ffi.lib.af_moments_combine_d(packed.device.index, stream, parts.data_ptr(), world, n,
+                                                 out.data_ptr()))
+    else:
+        cnt, s, ss = parts[:, 0].sum(0), parts[:, 1].sum(0), parts[:, 2].sum(0)
+        mean = s / cnt
+        out = torch.stack([cnt, mean, (ss / cnt - mean * mean).clamp_min(0.0),
+                           parts[:, 3].min(0).values, parts[:, 4].max(0).values])
+    return {"count": out[0], "mean": out[1], "var": out[2], "min": out[3], "max": out[4]}
 
 
 def shard(n_total, rank, world):

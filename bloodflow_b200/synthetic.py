@@ -63,6 +63,44 @@ def tree_param(order, Nx, Nt, N_cycles=1, Nt_store=None, N_cycles_store=1, Ru0=0
     return types.SimpleNamespace(param=param, geo=geo, solution=sol, fparams=None)
 
 
+# ---- UQ ensemble perturbation model ------------------------------------
+# Member ``i`` draws from numpy.random.Generator(PCG64(SEED + i)), in this order:
+#   s ~ U(0.9, 1.1) common factor on k1, k3; r ~ U(0.9, 1.1) factor on the root radius;
+#   R1, R2, CT ~ U(0.8, 1.2) per leaf.   (No device code here: bench.py's CPU reference arm uses it.)
+SEED = 20260000
+
+
+def member_factors(i, n_leaves, seed=SEED):
+    rng = np.random.Generator(np.random.PCG64(seed + int(i)))
+    s = rng.uniform(0.9, 1.1)
+    r = rng.uniform(0.9, 1.1)
+    return s, r, rng.uniform(0.8, 1.2, n_leaves), rng.uniform(0.8, 1.2, n_leaves), rng.uniform(0.8, 1.2, n_leaves)
+
+
+def perturb_param(param, i, seed=SEED):
+    """The member-``i`` version of a ParamParser-like description (a tree built
+    from ``alpha``): what a user would feed to ArteryNetwork for that member."""
+    import copy
+    p = copy.deepcopy(param)
+    n_l = len(np.atleast_1d(p.param['R1']))
+    s, r, f1, f2, fc = member_factors(i, n_l, seed)
+    p.param['k1'] = p.param['k1'] * s
+    p.param['k3'] = p.param['k3'] * s
+    p.param['Ru'] = np.array(p.param['Ru'], dtype=float)
+    p.param['Rd'] = np.array(p.param['Rd'], dtype=float)
+    nominal_leaf = leaf_radius(p.param['Ru'][0], p.param['alpha'], p.param['order']) if 'alpha' in p.param else None
+    untapered_leaves = nominal_leaf is not None and p.param['R_term'] == nominal_leaf
+    p.param['Ru'][0] *= r
+    p.param['Rd'][0] *= r
+    # leaves that are untapered in the nominal tree (R_term == leaf Ru bitwise, SURVEY F9) stay so
+    p.param['R_term'] = (leaf_radius(p.param['Ru'][0], p.param['alpha'], p.param['order']) if untapered_leaves
+                         else p.param['R_term'] * r)
+    p.param['R1'] = np.atleast_1d(p.param['R1']) * f1
+    p.param['R2'] = np.atleast_1d(p.param['R2']) * f2
+    p.param['CT'] = np.atleast_1d(p.param['CT']) * fc
+    return p
+
+
 def write_cfg(p, path):
     """Write a tree_param() description as a reference-format .cfg file."""
     def fmt(v):

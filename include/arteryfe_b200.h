@@ -42,6 +42,8 @@ extern "C" {
 #define AF_FLAG_PICARD_KMAX 4u    /* Windkessel Picard ran all k_max iterations (an:411, silent) */
 #define AF_FLAG_NONFINITE 8u      /* NaN/Inf in a residual norm */
 #define AF_FLAG_SINGULAR 16u      /* singular 18x18: the perturbation path an:703-708 was taken */
+#define AF_FLAG_PICARD_CYCLE 32u  /* Windkessel Picard ended in a round-off limit cycle: the reference runs all k_max
+                                     iterations there (an:411); the kernel returns the same value without them */
 
 /* what af_net_step stores at dump steps */
 #define AF_STORE_FLOW 1
@@ -125,7 +127,7 @@ int af_net_create(const af_desc* d, af_net** out);
 void af_net_destroy(af_net* net);
 
 /* Device and pinned-host blocks of destroyed / reconfigured handles are cached
- * (exact-size reuse, AF_CACHE_MB caps the device bytes, default 4096, 0 disables)
+ * (exact-size reuse, AF_CACHE_MB caps the device bytes, default 1024, 0 disables; recycled blocks are cleared)
  * so that loops over ArteryNetwork(param).solve() (the reference's way to run a
  * parameter study) do not pay cudaMalloc/cudaHostAlloc every time.  This call
  * returns everything cached to the driver. */
@@ -138,6 +140,15 @@ int af_release_cached_memory(void);
  * at the start of a step (state at t_n, an:924-938).  Enqueues only; no host
  * synchronisation. */
 int af_net_step(af_net* net, int64_t n_first, int64_t n_steps);
+
+/* Failure at the failing step (DOLFIN raises RuntimeError inside Artery.solve, ar:244): when the Newton
+ * solve of an artery of a SINGLE network does not converge (or goes non-finite) at global step g, every
+ * later launch of the loop returns at once and af_net_step stops enqueuing as soon as its polling (every
+ * 64 steps, no synchronisation) sees it.  af_net_failed_step waits for the stream and returns g, or -1.
+ * Ensemble members are independent: a failed member is flagged (af_net_get_flags), the others go on. */
+int af_net_failed_step(af_net* net, int64_t* step);
+/* Reset the status bits and the failed step (they are sticky otherwise). */
+int af_net_clear_flags(af_net* net);
 
 /* Wait for everything enqueued on the handle's stream. */
 int af_net_sync(af_net* net);
@@ -166,6 +177,15 @@ int af_net_fetch_snapshots(af_net* net, double* flow, double* area, double* pres
 /* Device pointer of the outlet-pressure store [max_snapshots][n_networks][n_leaves]
  * (for on-device ensemble statistics / NCCL reductions without a host copy). */
 int af_net_outlet_pressure_d(af_net* net, double** ptr_d);
+
+/* Ensemble statistics on the device: moments of the stored outlet pressures over the members
+ * of THIS handle, [5][n_snapshots*n_leaves] = count, sum, sum of squares, min, max (enqueued on the handle's
+ * stream; the buffer belongs to the handle).  Ranks exchange these packed buffers with ONE collective. */
+int af_net_outlet_moments_d(af_net* net, double** moments_d, int32_t* n_snapshots);
+/* Combine n_parts packed moment buffers ([n_parts][5][n], e.g. the all-gathered buffers of all ranks) into
+ * [5][n] = count, mean, variance, min, max on `device`, enqueued on `stream` (a cudaStream_t or NULL). */
+int af_moments_combine_d(int32_t device, void* stream, const double* parts_d, int32_t n_parts, int32_t n,
+                         double* out_d);
 
 /* Un of every artery (ar:154-158): A, q are [n_networks][n_arteries][Nx+1]. */
 int af_net_get_state(af_net* net, double* A, double* q);
@@ -230,6 +250,8 @@ int af_eval_cfl_term(af_net* net, int32_t network, int32_t artery, double x, dou
 int af_eval_math(int32_t device, int32_t which, int32_t n, const double* x, double* out);
 /* adjust_bifurcation_step (an:713-737): the common dex of one junction */
 int af_junction_cfl_dex(af_net* net, int32_t network, int32_t junction, double* dex);
+/* the same junction's min over the three CFL terms M (an:731-736); dex = (1 + margin) * dt / M */
+int af_junction_cfl_min(af_net* net, int32_t network, int32_t junction, double* M);
 /* problem_function / jacobian (an:476-665) at x[18] with the given dex of
  * (parent, d1, d2): y[18], J[18*18] row-major (either may be NULL) */
 int af_junction_eval(af_net* net, int32_t network, int32_t junction, const double dex[3], const double* x,

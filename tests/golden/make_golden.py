@@ -209,6 +209,21 @@ def golden_bc(net):
                 fx.append(net.problem_function(p, d1, d2, x))
                 Jx.append(net.jacobian(p, d1, d2, x))
                 xs.append(net.newton(p, d1, d2, x.copy()))
+            if n == BC_STEPS[1]:
+                # the 'Singular' branch of newton() (artery_network.py:701-708): with A^{n+1} of the three
+                # vessels at 1e300 the pressure-continuity rows 10, 11 of the Jacobian underflow to zero, LAPACK
+                # reports an exactly singular matrix and the reference perturbs (J + 1e-6 I, func[0] += 1e-6)
+                ip = net.range_parent_arteries[0]
+                i1, i2 = net.daughter_arteries(ip)
+                p, d1, d2 = net.arteries[ip], net.arteries[i1], net.arteries[i2]
+                x = xin[0].copy()
+                x[[9, 12, 15]] = 1.0e300
+                d['singular_x_in'] = x.copy()
+                d['singular_dex'] = np.array([p.dex, d1.dex, d2.dex])
+                said = io.StringIO()
+                with contextlib.redirect_stdout(said), np.errstate(all='ignore'):
+                    d['singular_newton_k1'] = net.newton(p, d1, d2, x.copy(), k_max=1)
+                assert 'Singular' in said.getvalue()
             d[tag + 'junction_dex'] = np.array(dexs)
             d[tag + 'x_in'] = np.array(xin)
             d[tag + 'problem_function'] = np.array(fx)

@@ -147,3 +147,26 @@ def test_shipped_configs_load(monkeypatch):
     an = af.ArteryNetwork(p)
     np.testing.assert_allclose(an.nondim['Ru'], [0.37, 0.296, 0.296])
     np.testing.assert_allclose(an.nondim['L'], [7.4, 5.92, 5.91])
+
+
+def test_unit_conversions_like_the_reference_tests():
+    """/root/reference/test/test_utils.py:8-17, same loops and constants."""
+    from bloodflow_b200.arteryfe.utils import is_near, mmHg_to_unit, unit_to_mmHg
+    for p in range(0, 30000, 500):
+        assert is_near(unit_to_mmHg(p), p / 1333.22368421053)
+    for p in range(0, 300, 5):
+        assert is_near(mmHg_to_unit(p), p * 1333.223684210535)
+
+
+def test_redimensionalise_inverts_nondimensionalise():
+    """utils.py:107-170: the four natures and the pass-through; the values of the demo cfg
+    (rc = 1, qc = 10, rho = 1.06) and of a non-unit scaling."""
+    from bloodflow_b200.arteryfe.utils import nondimensionalise, redimensionalise
+    x = np.array([0.0, 0.37, 4.1, 119990.131579])
+    for rc, qc, rho in ((1.0, 10.0, 1.06), (1.1, 9.0, 1.06)):
+        for nature, factor in (('time', qc / rc ** 3), ('area', 1 / rc ** 2), ('flow', 1 / qc),
+                               ('pressure', rc ** 4 / rho / qc ** 2)):
+            nd = nondimensionalise(rc, qc, rho, x, nature)
+            np.testing.assert_allclose(nd, x * factor, rtol=1e-15)
+            np.testing.assert_allclose(redimensionalise(rc, qc, rho, nd, nature), x, rtol=1e-15)
+        np.testing.assert_array_equal(redimensionalise(rc, qc, rho, x, 'anything else'), x)

@@ -184,7 +184,7 @@ def test_standalone_artery_like_the_reference_unit_tests():
         np.testing.assert_allclose(a.pn.values(), a.param['p0'] + a.f(xs) * (1 - np.sqrt(a.A0(xs) / A)), rtol=1e-12)
 
 
-@pytest.mark.parametrize('Nx', (2, 3, 5, 31, 127, 128, 129, 513))
+@pytest.mark.parametrize('Nx', (2, 3, 5, 31, 127, 128, 129, 513, 1500, 2047))     # 1500, 2047: the 512-thread CTA
 def test_vertex_counts_around_the_thread_mapping(Nx):
     """Four vertices per thread, T a power of two: every padding situation
     against the C oracle for 6 steps on an order-3 tree."""

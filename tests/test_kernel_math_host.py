@@ -166,3 +166,49 @@ def test_artery_assembly_and_newton(hh, case, step):
         assert its == a.newton_its
         np.testing.assert_allclose(A, a._U[:, 0], rtol=1e-11)
         np.testing.assert_allclose(q, a._U[:, 1], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('case', ('c1', 'c2', 'o3'))
+def test_singular_junction_branch(hh, case):
+    """The reference's 'Singular' branch (artery_network.py:701-708): golden vector produced by the
+    reference's own newton() (make_golden.py) on a state whose 18x18 Jacobian has two zero rows.
+    The hot path reports the vanished 3x3 pivot (-1), the verbatim dense path takes the perturbation
+    J + 1e-6 I, func[0] += 1e-6 and flags AF_FLAG_SINGULAR; the numpy oracle does the same."""
+    net, g = load_state(case, 3)
+    ip = net.range_parent_arteries[0]
+    i1, i2 = net.daughter_arteries(ip)
+    ves = [net.arteries[i] for i in (ip, i1, i2)]
+    vp = np.concatenate([vessel_params(a) for a in ves])
+    A = np.ascontiguousarray(np.array([a._Un[:, 0] for a in ves]))
+    q = np.ascontiguousarray(np.array([a._Un[:, 1] for a in ves]))
+    dex3 = np.ascontiguousarray(g['singular_dex'])
+    want = g['singular_newton_k1']
+    for a, d in zip(ves, dex3):
+        a.dex = d
+    with np.errstate(all='ignore'):
+        np.testing.assert_allclose(net.newton(*ves, g['singular_x_in'].copy(), k_max=1), want, rtol=1e-9)
+    fl = ctypes.c_uint(0)
+    xs = g['singular_x_in'].copy()
+    assert hh.hh_junction_newton(_dp(vp), ves[0].Nx, _dp(A), _dp(q), net.dt, _dp(dex3), _dp(xs), 1, 1e-10,
+                                 ctypes.byref(fl), 0) == -1
+    xs = g['singular_x_in'].copy()
+    assert hh.hh_junction_newton(_dp(vp), ves[0].Nx, _dp(A), _dp(q), net.dt, _dp(dex3), _dp(xs), 1, 1e-10,
+                                 ctypes.byref(fl), 1) == 1
+    assert fl.value & 16                      # AF_FLAG_SINGULAR
+    _check_perturbed_solve(net, ves, g['singular_x_in'], xs, want)
+
+
+def _check_perturbed_solve(net, ves, x_in, x_out, want):
+    """J + 1e-6 I has two rows that are 1e-6 on the diagonal and nothing else: cond ~ 1e9, so two
+    correct LU factorisations (LAPACK's in the reference, the 18x18 partial-pivot LU of the library)
+    agree to ~1e-5 of the largest entry only.  Forward: 1e-3 of the scale.  Backward (the meaningful
+    one): the update d = x_in - x_out satisfies (J + 1e-6 I) d = func + 1e-6 e_0 to round-off."""
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(x_out, want, rtol=0, atol=1e-3 * scale)
+    with np.errstate(all='ignore'):
+        J = net.jacobian(*ves, x_in.copy()) + 1e-6 * np.eye(18)
+        f = net.problem_function(*ves, x_in.copy())
+    f[0] += 1e-6
+    d = x_in - x_out
+    resid = J @ d - f
+    assert np.abs(resid).max() <= 1e-12 * np.abs(J).max() * np.abs(d).max()
