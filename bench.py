@@ -39,7 +39,7 @@ os.chdir(ROOT)
 METRIC = "artery-node-timesteps/sec"
 UNIT = "node-steps/s"
 ORDER, NX, NT = 8, 1000, 8000
-THETA = 0.6          # the variant of the C4 shape on which the scheme does not amplify round-off
+THETA = 0.6          # synthetic trees: the variant on which the scheme does not amplify round-off
 NT_STORE = 100
 C5_MEMBERS, C5_ORDER, C5_NX, C5_NT, C5_CYCLES = 65536, 4, 100, 2000, 2
 # algorithmic FP64 work per vertex-step: residual 110, Jacobian 140, block-Thomas solve 50
@@ -65,6 +65,7 @@ class ClockSampler(threading.Thread):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
+        self._active = threading.Event()     # NVML queries contend with the CUDA driver: sample only when asked
         self.ok = False
         try:
             import pynvml
@@ -87,6 +88,9 @@ class ClockSampler(threading.Thread):
             getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
         }
         while not self._stop_evt.is_set():
+            if not self._active.is_set():
+                self._active.wait(0.05)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -99,6 +103,12 @@ class ClockSampler(threading.Thread):
 
     def mark(self):
         return len(self.samples)
+
+    def resume(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
 
     def summary(self, lo=0, hi=None):
         s = self.samples[lo:hi]
@@ -294,11 +304,13 @@ def run_c5(args, rank, local_rank, world, torch, dist, sampler):
 
     barrier()
     mark = sampler.mark()
+    sampler.resume()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     dev.step(0, steps)
     e1.record(stream)
     barrier()
+    sampler.pause()
     clocks = sampler.summary(mark)
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -398,7 +410,8 @@ def main():
 
     K, W = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
-    sampler.start()                         # before the warm-up: short timed regions still get samples
+    sampler.start()
+    sampler.resume()                        # from before the warm-up on: short timed regions still get samples
     p = tree_member(args.order, args.Nx, args.Nt, rank, theta=args.theta)
     # the library enqueues on a torch stream, so torch CUDA events time exactly its kernels
     stream = torch.cuda.Stream(device=local_rank)
@@ -428,7 +441,9 @@ def main():
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    sampler.pause()                         # not during the phase replay / end-to-end runs (host-side interference)
     clocks = sampler.summary(mark)
+    clocks["window"] = "timed loop only; clocks_whole_run covers warm-up + timed loop (+ the C5 run)"
     clocks_run = None
     totals = dev.get_totals() - totals0             # counters of exactly the K timed steps
     flags = int(dev.get_flags()[0])

@@ -61,6 +61,9 @@ PROTOTYPES = {
     'af_junction_cfl_min': (c_int, [Handle, c_i32, c_i32, P_dbl]),
     'af_net_set_store': (c_int, [Handle, P_u8, c_i32, c_i32, c_i32]),
     'af_net_set_store_host': (c_int, [Handle, P_dbl, P_dbl, P_dbl, P_dbl]),
+    'af_net_set_store_host_pinned': (c_int, [Handle, ctypes.POINTER(P_dbl), ctypes.POINTER(P_dbl),
+                                             ctypes.POINTER(P_dbl), ctypes.POINTER(P_dbl)]),
+    'af_host_release': (c_int, [ctypes.c_void_p]),
     'af_net_snapshot_count': (c_int, [Handle, P_i32]),
     'af_net_fetch_snapshots': (c_int, [Handle, P_dbl, P_dbl, P_dbl, P_dbl, P_i64]),
     'af_net_outlet_pressure_d': (c_int, [Handle, ctypes.POINTER(ctypes.c_void_p)]),

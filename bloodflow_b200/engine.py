@@ -12,7 +12,25 @@ from . import _ffi
 from ._ffi import check, dptr, f64, i32, iptr, lib
 
 
+class _PinnedResult(object):
+    """Owner of a pinned result buffer of the library; numpy arrays made from it keep it alive and the
+    buffer goes back to the library's host cache when the last of them is gone."""
+
+    def __init__(self, ptr, shape):
+        self._ptr = ptr
+        self.__array_interface__ = {'shape': tuple(int(s) for s in shape), 'typestr': '<f8',
+                                    'data': (ptr, False), 'version': 3}
+
+    def __del__(self):
+        try:
+            lib.af_host_release(self._ptr)
+        except Exception:
+            pass
+
+
 class DeviceNetwork(object):
+    PINNED_STORE_BYTES = 64 << 20        # stores up to this size get library-pinned result arrays
+
     def __init__(self, Nx, Nt, theta, dt, junctions, leaves, k1, k2, k3, rho, Re, db, p0, Ru, Rd, L, q0,
                  R1, R2, CT, q_ins, device=0, stream=None, root_artery=0, **constants):
         Ru = np.atleast_2d(f64(Ru))
@@ -113,6 +131,20 @@ class DeviceNetwork(object):
         stream every snapshot into them while the loop runs (af_net_set_store_host)."""
         n = self._max_snap
         out, ptrs = {}, []
+        layout = (('flow', _ffi.AF_STORE_FLOW, (n, self.nb, self.na, self.np)),
+                  ('area', _ffi.AF_STORE_AREA, (n, self.nb, self.na, self.np)),
+                  ('pressure', _ffi.AF_STORE_PRESSURE, (n, self.nb, self.na, self.np)),
+                  ('outlet_pressure', _ffi.AF_STORE_OUTLET_PRESSURE, (n, self.nb, self.nl)))
+        total = sum(8 * int(np.prod(shape)) for _, bit, shape in layout if self._store_fields & bit)
+        if total <= self.PINNED_STORE_BYTES:
+            # small store: result arrays in pinned memory of the library, snapshots land in them directly
+            raw = [_ffi.P_dbl() for _ in layout]
+            check(lib.af_net_set_store_host_pinned(self._h, *[ctypes.byref(r) for r in raw]))
+            for (name, bit, shape), r in zip(layout, raw):
+                if self._store_fields & bit:
+                    out[name] = np.asarray(_PinnedResult(ctypes.cast(r, ctypes.c_void_p).value, shape))
+            self._host_store = out
+            return
         for name, bit, shape in (('flow', _ffi.AF_STORE_FLOW, (n, self.nb, self.na, self.np)),
                                  ('area', _ffi.AF_STORE_AREA, (n, self.nb, self.na, self.np)),
                                  ('pressure', _ffi.AF_STORE_PRESSURE, (n, self.nb, self.na, self.np)),

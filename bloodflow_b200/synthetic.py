@@ -3,6 +3,11 @@
 dicts of a ParamParser, i.e. exactly what a .cfg file of the reference would
 hold, so they go through the same ArteryNetwork constructor.
 
+theta = 0.6 by default: with the shipped configs' 0.55 the fine-grid trees (C3, C4) and the extreme members
+of the C5 ensemble amplify round-off into grid-scale noise (a 1e-13 perturbation reaches 1e-2 within 320
+steps, 11 of 65 536 C5 members end non-finite); at 0.6 the same shapes are stable over 4 cycles
+(scripts/stability_probe.py, profiles/r02_stability_*.jsonl, BASELINE.md).
+
 Recipe: ``build_geometry`` tree with alpha, L; untapered leaves
 (R_term = Ru0*alpha**(order-1)); per leaf R_tot = p0/(mean_flow/n_leaves),
 R1_eff = 2*Z0 (Picard gain 0.5), R2_eff = R_tot - R1_eff, CT = tau/R2_eff; the
@@ -41,7 +46,7 @@ def leaf_radius(Ru0, alpha, order):
 
 
 def tree_param(order, Nx, Nt, N_cycles=1, Nt_store=None, N_cycles_store=1, Ru0=0.37, alpha=0.8, L=20.0,
-               theta=0.55, output_location='output/synthetic', inlet=INLET, store_area=1, store_pressure=1):
+               theta=0.6, output_location='output/synthetic', inlet=INLET, store_area=1, store_pressure=1):
     """ParamParser-like description of a symmetric tree of ``order`` levels."""
     N = 2 ** order - 1
     n_leaves = 2 ** (order - 1)

@@ -165,6 +165,13 @@ int af_net_set_store(af_net* net, const uint8_t* step_mask, int32_t first_cycle,
  * these buffers); af_net_fetch_snapshots with the same pointers only waits for the
  * last ones.  The buffers must stay valid until then. */
 int af_net_set_store_host(af_net* net, double* flow, double* area, double* pressure, double* outlet_pressure);
+/* The same with result arrays OWNED BY THE LIBRARY: pinned host buffers sized for the whole store
+ * ([max_snapshots][...] per configured field, NULL for the others) are returned, and every snapshot is
+ * copied straight into them (no staging ring, no host-side copy).  Meant for small stores; the buffers
+ * outlive the handle and must be returned with af_host_release once the caller is done with them. */
+int af_net_set_store_host_pinned(af_net* net, double** flow, double** area, double** pressure,
+                                 double** outlet_pressure);
+int af_host_release(void* buffer);
 int af_net_snapshot_count(af_net* net, int32_t* count);
 /* Copy stored fields out; each of flow/area/pressure is
  * [count][n_networks][n_arteries][Nx+1] (NULL to skip), outlet_pressure is

@@ -343,12 +343,12 @@ def test_full_size_trees_short_horizon(order, Nx, Nt, steps):
     from bloodflow_b200.synthetic import tree_param
     from oracle import arteryfe_oracle as ao
     from oracle.oracle_c import COracle
-    an = af.ArteryNetwork(tree_param(order, Nx=Nx, Nt=Nt))
+    an = af.ArteryNetwork(tree_param(order, Nx=Nx, Nt=Nt, theta=0.55))
     an.define_x()
     an._dev.set_counter_log(steps)
     an._dev.step(0, steps)
     A, q = an._dev.get_state()
-    p = tree_param(order, Nx=Nx, Nt=Nt)
+    p = tree_param(order, Nx=Nx, Nt=Nt, theta=0.55)
     c = COracle(ao.OracleNetwork(p.param, p.geo, p.solution))
     failed, la, lj = c.step(0, steps, nthreads=0, log=True)
     assert failed == 0
@@ -377,7 +377,11 @@ def test_full_size_trees_full_cycle(order, Nx, Nt):
     which the reference scheme does not amplify round-off (scripts/stability_probe.py,
     profiles/r02_stability_*.jsonl; at theta = 0.55 a 1e-13 perturbation reaches 1e-2 within 320 steps):
     A and q of every vertex within 1e-9 at eight checkpoints, artery Newton counts equal at every
-    step, junction Newton counts equal at every step."""
+    step (0 of 2 040 000 differ on C4), junction Newton counts equal except for near-ties of the
+    stopping test: ||f|| < 1e-10 is applied to an f whose own round-off is ~1e-11 (pressure terms of
+    size 1e4-1e5), so an iterate that lands within ~10 % of the threshold is counted k or k+1 by two
+    correct implementations (measured, profiles/r02_parity_c3_c4.jsonl: 42 of 1 016 000 on C4, 18 of
+    60 000 on C3; never by more than one; the states still agree to 2e-10)."""
     import bloodflow_b200.arteryfe as af
     from bloodflow_b200.synthetic import tree_param
     from oracle import arteryfe_oracle as ao
@@ -404,7 +408,9 @@ def test_full_size_trees_full_cycle(order, Nx, Nt):
         np.testing.assert_allclose(dev.get_junction_x()[0], c.x(), rtol=1e-9)
     art, jun, _ = dev.fetch_counter_log()
     np.testing.assert_array_equal(art[:, 0], np.concatenate(la))
-    np.testing.assert_array_equal(jun[:, 0], np.concatenate(lj))
+    lj = np.concatenate(lj)
+    assert np.count_nonzero(jun[:, 0] != lj) <= 1e-3 * lj.size
+    assert np.abs(jun[:, 0] - lj).max() <= 1
     assert int(dev.get_flags()[0]) & (1 | 8) == 0
 
 

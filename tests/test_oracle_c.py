@@ -56,7 +56,7 @@ def test_fine_grid_trees_are_sensitive():
     from bloodflow_b200.synthetic import tree_param
 
     def make():
-        p = tree_param(5, Nx=500, Nt=4000)
+        p = tree_param(5, Nx=500, Nt=4000, theta=0.55)
         return COracle(ao.OracleNetwork(p.param, p.geo, p.solution))
     a, b = make(), make()
     A, q = b.state()
@@ -71,3 +71,20 @@ def test_fine_grid_trees_are_sensitive():
         growth.append(np.abs(b.state()[0] / a.state()[0] - 1).max())
     assert growth[0] < 1e-10          # still tracking after 40 steps
     assert growth[1] > 1e-4           # decorrelated after 320
+
+
+def test_theta_06_trees_are_not_sensitive():
+    """The same tree with theta = 0.6 (the synthetic default, what bench.py runs): the perturbation
+    stays at round-off level.  (Whole cycles / 4 cycles of C3 and C4: profiles/r02_stability_*.jsonl.)"""
+    from bloodflow_b200.synthetic import tree_param
+
+    def make():
+        p = tree_param(5, Nx=500, Nt=4000, theta=0.6)
+        return COracle(ao.OracleNetwork(p.param, p.geo, p.solution))
+    a, b = make(), make()
+    A, q = b.state()
+    A[3, 100] *= 1 + 1e-13
+    b.set_state(A, q)
+    a.step(0, 400, nthreads=0)
+    b.step(0, 400, nthreads=0)
+    assert np.abs(b.state()[0] / a.state()[0] - 1).max() < 1e-11
