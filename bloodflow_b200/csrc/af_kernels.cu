@@ -489,69 +489,27 @@ __device__ __forceinline__ Elim unpark(const double* base, int T, int t) {
   return e;
 }
 
-// Thread <-> vertex-block mapping.  A thread owns the four consecutive vertices 4j .. 4j+3 of block j
-// and, after the register levels of the cyclic reduction, row j of the T-row reduced system.  Which
-// thread owns which block is chosen so that every later level of the reduction works on WHOLE WARPS:
-//   rows with  j = 2^z - 1 (mod 2^(z+1))  -- the ones cyclic-reduction level z eliminates -- live in the
-//   threads [T - (T >> z), T - (T >> (z+1))),  z = 0 .. LV-1,  LV = log2(T) - 5;
-//   the 32 rows that survive all LV levels (j = 2^LV - 1 mod 2^LV) live in the last warp.
-// (T = 256: even blocks in warps 0-3, j = 1 mod 4 in warps 4-5, j = 3 mod 8 in warp 6, j = 7 mod 8 in warp 7.)
-// A level then costs issue slots only in the warps that have work, where the previous parallel cyclic
-// reduction kept all T rows busy for log2(T) steps (~half of the FP64 instructions of a solve pass).
-// The one-warp kernel (T = 32) has nothing to compact: identity mapping.
+// The iterate U lives in shared memory with the four vertices of a thread in four
+// planes: vertex i at [(i & 3) * T + (i >> 2)].  A warp reading "its" vertex k (or
+// the neighbouring thread's) touches 32 consecutive doubles: no bank conflicts
+// (the natural order, stride 4 doubles per thread, is a 4-way conflict on every
+// access -- 0.96 M conflicts per launch in profiles/r01_final_ncu_full_summary.txt).
 template <int T>
-struct Map {
-  static constexpr int M = (T == 32 ? 5 : T == 64 ? 6 : T == 128 ? 7 : T == 256 ? 8 : 9);
-  static constexpr int LV = M - 5;
-  __device__ __forceinline__ static int blk_of(int t) {
-    if (T == 32) return t;
-    const int v = T - 1 - t;                            // 0 .. T-1 from the end
-    int z = v ? (M - 32 + __clz(v)) : LV;               // level of thread t (>= LV: last warp)
-    if (z >= LV) return ((t - (T - 32)) << LV) + (1 << LV) - 1;
-    return ((t - (T - (T >> z))) << (z + 1)) + (1 << z) - 1;
-  }
-  __device__ __forceinline__ static int thr_of(int j) {
-    if (T == 32) return j;
-    const int z = __ffs(~j) - 1;                        // trailing ones of j
-    if (z >= LV) return T - 32 + (j >> LV);
-    return T - (T >> z) + (j >> (z + 1));
-  }
-};
-
-// what a thread needs to know about its place: its block and the threads of the neighbouring blocks
-struct Lane {
-  int tid, blk, tl, tr;       // tl / tr = tid where the neighbour does not exist (never dereferenced for data)
-};
+__device__ __forceinline__ int vix(int i) { return (i & 3) * T + (i >> 2); }
 
 template <int T>
-__device__ __forceinline__ Lane make_lane() {
-  Lane l;
-  l.tid = threadIdx.x;
-  l.blk = Map<T>::blk_of(l.tid);
-  l.tl = l.blk > 0 ? Map<T>::thr_of(l.blk - 1) : l.tid;
-  l.tr = l.blk + 1 < T ? Map<T>::thr_of(l.blk + 1) : l.tid;
-  return l;
-}
-
-// The iterate U lives in shared memory in four planes: vertex k (0..3) of the block of thread t at
-// [k * T + t].  A warp touching "its" vertex k reads 32 consecutive doubles (no bank conflicts).
-template <int T>
-__device__ __forceinline__ void row_of(const ArteryCtx& c, const Lane& ln, int k, bool first, const double* sA,
-                                       const double* sq, const CellInt& left, const CellInt& own, double& EA,
-                                       double& Eq, Row& row) {
+__device__ __forceinline__ void row_of(const ArteryCtx& c, int i, bool first, const double* sA, const double* sq,
+                                       const CellInt& left, const CellInt& own, double& EA, double& Eq, Row& row) {
   // a neighbour that does not exist is replaced by the vertex itself (build_row ignores it)
-  const int j0 = k * T + ln.tid;
-  const int jm = k > 0 ? j0 - T : (ln.blk > 0 ? 3 * T + ln.tl : j0);
-  const int jp = k < 3 ? j0 + T : (ln.blk + 1 < T ? ln.tr : j0);
-  build_row<true>(c, 4 * ln.blk + k, first, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], left, own, EA, Eq, row);
+  const int jm = vix<T>(i > 0 ? i - 1 : i), j0 = vix<T>(i), jp = vix<T>(i < 4 * T - 1 ? i + 1 : i);
+  build_row<true>(c, i, first, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], left, own, EA, Eq, row);
 }
 
 template <int T, bool JAC>
-__device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const Lane& ln, const CellCoef& ccu,
-                                               const double* tab, int S, const double* sA, const double* sq, int k) {
+__device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
+                                               const double* sA, const double* sq, int i) {
   CellInt ci;
   cell_zero(ci);
-  const int i = 4 * ln.blk + k;
   if (i < c.ne) {
     CellCoef cc = ccu;
     if (tab) {
@@ -562,7 +520,7 @@ __device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const Lane& l
         cc.t3[g] = tab[(6 + g) * S + i];
       }
     }
-    const int jl = k * T + ln.tid, jr = k < 3 ? jl + T : ln.tr;      // right vertex of the last cell: next block's a
+    const int jl = vix<T>(i), jr = vix<T>(i + 1);
     ci = cell_integrals<JAC>(c.h, c.Kr, cc, sA[jl], sA[jr], sq[jl], sq[jr]);
   }
   return ci;
@@ -573,10 +531,10 @@ __device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const Lane& l
 // depend on the iterate U only (not on the Dirichlet data), go to shared memory:
 // cell k of thread t into slot t of region k (pa, pb, pc, lo; 10 doubles each).
 template <int T>
-__device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const Lane& ln, const CellCoef& ccu,
-                                              const double* tab, int S, const double* sA, const double* sq,
-                                              double* pa, double* pb, double* pc, double* lo) {
-  const int tid = ln.tid;
+__device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
+                                              const double* sA, const double* sq, double* pa, double* pb,
+                                              double* pc, double* lo) {
+  const int tid = threadIdx.x, i0 = 4 * tid;
   if (T == 32) {
     // one-warp (ensemble) kernel: ONE copy of the cell routine, executed four times.
     // With 16 independent one-warp CTAs per SM the instruction cache, not ILP, is
@@ -584,7 +542,7 @@ __device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const Lane& ln
     // regions are contiguous: lo | pa | pb | pc, cell k -> region (k + 1) % 4
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-      CellInt ci = artery_cell<T, true>(c, ln, ccu, tab, S, sA, sq, k);
+      CellInt ci = artery_cell<T, true>(c, ccu, tab, S, sA, sq, i0 + k);
       double* r = lo + ((k + 1) & 3) * 10 * T;
       r[0 * T + tid] = ci.Gl; r[1 * T + tid] = ci.Gr;
 #pragma unroll
@@ -595,7 +553,7 @@ __device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const Lane& ln
   double* reg[4] = {pa, pb, pc, lo};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    CellInt ci = artery_cell<T, true>(c, ln, ccu, tab, S, sA, sq, k);
+    CellInt ci = artery_cell<T, true>(c, ccu, tab, S, sA, sq, i0 + k);
     double* r = reg[k];
     r[0 * T + tid] = ci.Gl; r[1 * T + tid] = ci.Gr;
 #pragma unroll
@@ -622,23 +580,23 @@ __device__ __forceinline__ void load_cell_right_part(const double* r, int T, int
 // part).  This is done before the convergence test is known; on the converged
 // pass it is discarded.  Returns the thread's share of ||R||^2.
 template <int T>
-__device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const Lane& ln, const double* sA, const double* sq,
-                                                 double* pa, double* pb, double* pc, const double* lo, bool first,
-                                                 double* EA, double* Eq, Row& rb, Row& rd) {
-  const int tid = ln.tid;
+__device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const double* sA, const double* sq, double* pa,
+                                                 double* pb, double* pc, const double* lo, bool first, double* EA,
+                                                 double* Eq, Row& rb, Row& rd) {
+  const int tid = threadIdx.x, i0 = 4 * tid;
   CellInt left, own;
   cell_zero(left);
   cell_zero(own);
   double part = 0.0;
-  if (ln.blk > 0) load_cell_right_part(lo, T, ln.tl, left);    // last cell of the previous block
+  if (tid > 0) load_cell_right_part(lo, T, tid - 1, left);     // last cell of the previous thread
   load_cell_left_part(pa, T, tid, own);
   {
     Row ra;
-    row_of<T>(c, ln, 0, first, sA, sq, left, own, EA[0], Eq[0], ra);
+    row_of<T>(c, i0, first, sA, sq, left, own, EA[0], Eq[0], ra);
     part += ra.r[0] * ra.r[0] + ra.r[1] * ra.r[1];
     load_cell_right_part(pa, T, tid, left);
     load_cell_left_part(pb, T, tid, own);
-    row_of<T>(c, ln, 1, first, sA, sq, left, own, EA[1], Eq[1], rb);
+    row_of<T>(c, i0 + 1, first, sA, sq, left, own, EA[1], Eq[1], rb);
     part += rb.r[0] * rb.r[0] + rb.r[1] * rb.r[1];
     Elim ea = make_elim(ra);
     park(pa, T, tid, ea);
@@ -648,11 +606,11 @@ __device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const Lane&
     Row rc;
     load_cell_right_part(pb, T, tid, left);
     load_cell_left_part(pc, T, tid, own);
-    row_of<T>(c, ln, 2, first, sA, sq, left, own, EA[2], Eq[2], rc);
+    row_of<T>(c, i0 + 2, first, sA, sq, left, own, EA[2], Eq[2], rc);
     part += rc.r[0] * rc.r[0] + rc.r[1] * rc.r[1];
     load_cell_right_part(pc, T, tid, left);
     load_cell_left_part(lo, T, tid, own);
-    row_of<T>(c, ln, 3, first, sA, sq, left, own, EA[3], Eq[3], rd);
+    row_of<T>(c, i0 + 3, first, sA, sq, left, own, EA[3], Eq[3], rd);
     part += rd.r[0] * rd.r[0] + rd.r[1] * rd.r[1];
     Elim ec = make_elim(rc);
     park(pc, T, tid, ec);
@@ -683,19 +641,20 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   // A failed artery solve of an earlier step ends a single-network run (DOLFIN raises there,
   // ar:244).  The previous artery kernel has completed before this one can start (the boundary
   // kernel between them waits for it before it triggers), so its fail_step is visible here.
-  if (nd.stop_on_fail && *nd.fail_step != AF_NO_FAIL) return;
+  // (not in the one-warp kernel, whose register budget it would break: there the boundary kernel's
+  // early return and the host's polling end the run)
+  if (T > 32 && nd.stop_on_fail && *nd.fail_step != AF_NO_FAIL) return;
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
-  const Lane ln = make_lane<T>();
   {
     // U <- Un (ar:158; the Newton initial guess is the previous solution)
     const double* gA = nd.A[cur] + off;
     const double* gq = nd.q[cur] + off;
-    // each thread fetches the four vertices of its block (two 16-byte loads per field, whole
-    // 32-byte sectors); the rows of an artery start 256-byte aligned
-    const int i0 = 4 * ln.blk;
+    // each thread fetches its own four vertices (two 16-byte loads per field: a warp
+    // reads 1 KB contiguously); the rows of an artery start 256-byte aligned
+    const int i0 = 4 * tid;
     double va[4] = {1.0, 1.0, 1.0, 1.0}, vq[4] = {0.0, 0.0, 0.0, 0.0};     // padding vertices
     if (i0 + 3 < np) {
       const double2 a01 = *reinterpret_cast<const double2*>(gA + i0), a23 = *reinterpret_cast<const double2*>(gA + i0 + 2);
@@ -795,7 +754,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     // of the assembly code costs more instruction-cache misses than the skipped
     // derivative terms save (tree 59.3 -> 57.7 us/step, ensemble +8 % without it).
     Row rb, rd;
-    cells_to_smem<T>(c, ln, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
+    cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
     if (!FUSED && first) {
       // Everything up to here (vessel constants, U <- Un, the cell integrals of the
       // first pass) only needs the previous artery kernel's output and has been
@@ -811,7 +770,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       }
     }
     cta_sync<T>();
-    double part = rows_from_smem<T>(c, ln, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
+    double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
     const double r2 = block_sum<T>(part, red);    // its two barriers also publish pa/pc
     const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
     // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ------------------
@@ -820,8 +779,8 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
     if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
     // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------
-    if (ln.blk + 1 < T) {
-      Elim en = unpark(pa, T, ln.tr);        // vertex a of the next block
+    if (tid + 1 < T) {
+      Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
       apply_right(rd, en);
     }
     {
@@ -830,70 +789,20 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       apply_left(rd, eb);
     }
     cta_sync<T>();
-    if (ln.blk + 1 < T) {
-      Elim en = unpark(pb, T, ln.tr);        // vertex b of the next block
+    if (tid + 1 < T) {
+      Elim en = unpark(pb, T, tid + 1);      // vertex b of the next thread
       apply_right(rd, en);
     }
-    // ---- the reduced system: row j = ln.blk, one per thread, kept in registers ----------
+    // ---- the reduced system (one row per thread): parallel cyclic reduction ---
+    // The row stays in registers.  In step s = 1, 2, 4, ... every thread turns
+    // its row into x_t = g - P x_{t-s} - Q x_{t+s}, publishes (P, Q, g) and
+    // eliminates both neighbours at distance s; after log2(T) steps the rows are
+    // decoupled.  All warps stay busy and there is no backward sweep: on this
+    // latency-bound kernel the shorter serial chain beats the work-optimal
+    // cyclic reduction (profiles/README.md).
     double xd[2], xl[2] = {0.0, 0.0};
-    double* buf = Lo;                         // 10T doubles: Elim of an eliminated row in the slot of its thread
-    if (T > 32) {
-      // Cyclic reduction over whole warps (see Map): level z eliminates the rows of the threads
-      // [base, base + cnt); the rows that remain (all in later threads) absorb their two eliminated
-      // neighbours, which sit in consecutive threads of that range.  One barrier per level.
-      int base = 0;
-#pragma unroll
-      for (int z = 0; z < Map<T>::LV; ++z) {
-        const int cnt = T >> (z + 1);
-        if (tid >= base && tid < base + cnt) park(buf, T, tid, make_elim(rd));
-        cta_sync<T>();
-        if (tid >= base + cnt) {
-          const int ql = ln.blk >> (z + 1);               // left neighbour j - 2^z is the ql-th row of the level
-          apply_left(rd, unpark(buf, T, base + ql));
-          if (ql + 1 < cnt) apply_right(rd, unpark(buf, T, base + ql + 1));
-        }
-        base += cnt;
-      }
-      // the last 32 rows (one warp): parallel cyclic reduction, 5 steps, warp-level barriers only
-      if (tid >= T - 32) {
-        const int lane = tid - (T - 32);
-#pragma unroll 1
-        for (int sdist = 1; sdist < 32; sdist *= 2) {
-          park(buf, T, tid, make_elim(rd));
-          __syncwarp();
-          const bool more = 2 * sdist < 32;
-          if (lane >= sdist) apply_left(rd, unpark(buf, T, tid - sdist), more);
-          if (lane + sdist < 32) apply_right(rd, unpark(buf, T, tid + sdist), more);
-          __syncwarp();
-        }
-        double inv[4];
-        inv2v(rd.dg, inv);
-        xd[0] = inv[0] * rd.r[0] + inv[1] * rd.r[1];
-        xd[1] = inv[2] * rd.r[0] + inv[3] * rd.r[1];
-        buf[8 * T + tid] = xd[0]; buf[9 * T + tid] = xd[1];      // x of a row lives in the g slot of its thread
-      }
-      // back-substitution, deepest level first: x_j = g - P x_(j-s) - Q x_(j+s), both already known
-      base = T - 32;
-#pragma unroll
-      for (int z = Map<T>::LV - 1; z >= 0; --z) {
-        const int cnt = T >> (z + 1), s = 1 << z;
-        base -= cnt;
-        cta_sync<T>();
-        if (tid >= base && tid < base + cnt) {
-          const Elim e = unpark(buf, T, tid);
-          double xa_[2] = {0.0, 0.0}, xb_[2];
-          if (ln.blk >= s) { const int t2 = Map<T>::thr_of(ln.blk - s); xa_[0] = buf[8 * T + t2]; xa_[1] = buf[9 * T + t2]; }
-          { const int t2 = Map<T>::thr_of(ln.blk + s); xb_[0] = buf[8 * T + t2]; xb_[1] = buf[9 * T + t2]; }
-          back_sub(e, xa_, xb_, xd);
-          buf[8 * T + tid] = xd[0]; buf[9 * T + tid] = xd[1];
-        }
-      }
-      cta_sync<T>();
-      if (ln.blk > 0) { xl[0] = buf[8 * T + ln.tl]; xl[1] = buf[9 * T + ln.tl]; }
-    } else {
-      // one-warp kernel: parallel cyclic reduction over its 32 rows.  In step s = 1, 2, 4, ...
-      // every thread turns its row into x_t = g - P x_{t-s} - Q x_{t+s}, publishes (P, Q, g) and
-      // eliminates both neighbours at distance s; after 5 steps the rows are decoupled.
+    {
+      double* buf = Lo;                       // 10T doubles of the 14T scratch
 #pragma unroll 1
       for (int sdist = 1; sdist < T; sdist *= 2) {
         park(buf, T, tid, make_elim(rd));
@@ -929,7 +838,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   {
     double* gA = nd.A[cur ^ 1] + off;
     double* gq = nd.q[cur ^ 1] + off;
-    const int i0 = 4 * ln.blk;
+    const int i0 = 4 * tid;
     if (i0 + 3 < np) {
       *reinterpret_cast<double2*>(gA + i0) = make_double2(sA[tid], sA[T + tid]);
       *reinterpret_cast<double2*>(gA + i0 + 2) = make_double2(sA[2 * T + tid], sA[3 * T + tid]);

@@ -284,7 +284,7 @@ def test_ensemble_members_are_independent():
                  for ip in an0.range_parent_arteries]
     leaves = [an0._compact[i] for i in an0.range_leaf_arteries]
     dev = DeviceNetwork(
-        64, 800, 0.55, an0.dt, junctions, leaves,
+        64, 800, an0.sol['theta'], an0.dt, junctions, leaves,
         k1=[an.nondim['k1'] for an in descs], k2=an0.nondim['k2'], k3=[an.nondim['k3'] for an in descs],
         rho=an0.nondim['rho'], Re=an0.nondim['Re'], db=ex[0][0].db, p0=an0.nondim['p0'],
         Ru=[[a._Ru for a in e] for e in ex], Rd=[[a._Rd for a in e] for e in ex], L=[[a._L for a in e] for e in ex],
@@ -315,7 +315,9 @@ def test_ensemble_driver_matches_single_member_runs():
         an = af.ArteryNetwork(en.perturb_param(base, i))
         res = an.solve(write_output=False)
         leaf_p = np.array([res['pressure'][:, an._compact[k], -1] for k in an.range_leaf_arteries]).T
-        np.testing.assert_allclose(op[:, m, :], leaf_p, rtol=1e-12)
+        # the stacked description and the facade differ in the last bit of some lengths (different
+        # but equivalent expressions): round-off level agreement, not bitwise
+        np.testing.assert_allclose(op[:, m, :], leaf_p, rtol=1e-10)
     # statistics: the library's moments kernel + fold kernel (one rank: no collective)
     packed = en.device_moments(ens.dev, 0)
     assert tuple(packed.shape) == (5, 40, 4)
