@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get('ARTERYFE_B200_LIB') or os.path.join(_HERE, 'csrc', 'l
 AF_ABI_VERSION = 1
 AF_OK, AF_EINVAL, AF_ENODEVICE, AF_ECUDA, AF_ENOMEM, AF_ESTATE = 0, -1, -2, -3, -4, -5
 AF_FLAG_ARTERY_NOCONV, AF_FLAG_JUNCTION_KMAX, AF_FLAG_PICARD_KMAX = 1, 2, 4
-AF_FLAG_NONFINITE, AF_FLAG_SINGULAR, AF_FLAG_PICARD_CYCLE = 8, 16, 32
+AF_FLAG_NONFINITE, AF_FLAG_SINGULAR, AF_FLAG_PICARD_CYCLE, AF_FLAG_SYNC_TIMEOUT = 8, 16, 32, 64
 AF_STORE_FLOW, AF_STORE_AREA, AF_STORE_PRESSURE, AF_STORE_OUTLET_PRESSURE = 1, 2, 4, 8
 
 c_int, c_i32, c_i64, c_dbl = ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_double

@@ -32,6 +32,30 @@ using namespace af;
 
 #define AF_NO_FAIL 0xffffffffffffffffull
 
+// ---- release / acquire flags in global memory (the semaphore pattern: one thread of the producer
+// releases after a CTA / warp barrier, one thread of the consumer acquires before one) ----
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spin until *p >= want.  A failed run (fail_step set) ends every wait -- the producer may have left
+// early; so does an absurdly long wait (~1 s), which is reported as AF_FLAG_SYNC_TIMEOUT instead of
+// hanging the device.
+#define AF_FLAG_SYNC_TIMEOUT 64u
+__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned want, const unsigned long long* fail_step,
+                                          uint32_t* status) {
+  for (unsigned spins = 0; (int)(ld_acquire_u32(p) - want) < 0; ++spins) {
+    if ((spins & 63u) == 63u) {
+      if (*(volatile const unsigned long long*)fail_step != AF_NO_FAIL) return;
+      if (spins > (1u << 23)) { atomicOr(status, AF_FLAG_SYNC_TIMEOUT); return; }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // device view
 // ---------------------------------------------------------------------------
@@ -66,6 +90,14 @@ struct NetDev {
   uint32_t* flags;             // [nb]
   unsigned long long* fail_step;  // [1] first global step at which an artery Newton failed (AF_NO_FAIL: none)
   int stop_on_fail;            // single networks: every later launch returns at once (DOLFIN raises, ar:244)
+  // Dataflow between the kernels of the time loop (single networks, T >= 64): instead of waiting for the
+  // whole previous grid, a task waits for exactly the arteries / junctions it depends on.
+  //   f_art[ba] = number of time steps artery ba has completed (g + 1 after step g)
+  //   f_in[ba], f_out[ba] = g + 1 once the Dirichlet data of the inlet / outlet end for step g is written
+  unsigned* f_art;
+  unsigned* f_in;
+  unsigned* f_out;
+  int dataflow;
   // solver constants
   double newton_rtol, newton_atol;
   int newton_max_it, junction_k_max, picard_k_max;
@@ -162,7 +194,8 @@ __global__ void k_setup_x(NetDev nd, const double* q0) {
 // ---------------------------------------------------------------------------
 // common tail of a junction task: write x, the Dirichlet data and the counters
 __device__ __forceinline__ void junction_finish(const NetDev& nd, int b, int j, const int* ia, const double* x,
-                                                double dex, int solves, uint32_t fl, int log_slot) {
+                                                double dex, int solves, uint32_t fl, int log_slot,
+                                                long long flag_step = -1) {
   double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
   for (int i = 0; i < 18; ++i) xg[i] = x[i];
   // set_inner_bc (an:762-764)
@@ -175,6 +208,12 @@ __device__ __forceinline__ void junction_finish(const NetDev& nd, int b, int j, 
   if (log_slot >= 0) nd.log_j[(size_t)log_slot * nd.nb * nd.nj + b * nd.nj + j] = solves;
   atomicAdd(&nd.totals[1], (unsigned long long)solves);
   if (fl) atomicOr(&nd.flags[b], fl);
+  if (flag_step >= 0) {        // dataflow: the three artery ends may go on (one thread wrote everything above)
+    __threadfence();
+    st_release_u32(&nd.f_out[bp], (unsigned)(flag_step + 1));
+    st_release_u32(&nd.f_in[b1], (unsigned)(flag_step + 1));
+    st_release_u32(&nd.f_in[b2], (unsigned)(flag_step + 1));
+  }
 }
 
 // verbatim dense path (reference formulas, 18x18 LU): owns the singular branch an:703-708
@@ -292,14 +331,14 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
 }
 
 __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, const int* ia,
-                                                   const Vessel& ves, int log_slot) {
+                                                   const Vessel& ves, int log_slot, long long flag_step = -1) {
   double x[18], dex;
   int solves;
   uint32_t fl;
   const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
   junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl);
   if ((threadIdx.x & 31) != 0) return;
-  junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot);
+  junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot, flag_step);
 }
 
 __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int l, int log_slot) {
@@ -320,7 +359,7 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
 // L-2dex, L-dex, L of windkessel() (an:383-390), lanes 0..1 the two half steps
 // (an:393-398); the Picard loop is inherently serial.
 __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, int b, int l, int ba,
-                                                    const Vessel& ves, int log_slot) {
+                                                    const Vessel& ves, int log_slot, long long flag_step = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = lane % 3;
@@ -367,6 +406,10 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
   atomicAdd(&nd.totals[2], (unsigned long long)r.its);
   if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)(r.cycle ? AF_FLAG_PICARD_CYCLE : AF_FLAG_PICARD_KMAX));
+  if (flag_step >= 0) {
+    __threadfence();
+    st_release_u32(&nd.f_out[ba], (unsigned)(flag_step + 1));
+  }
   return r;
 }
 
@@ -376,7 +419,7 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
 // (ensembles).  Two instantiations keep each kernel's code -- and the instruction
 // cache footprint of the lone warp that runs a task -- small.
 template <bool WARP>
-__global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl) {
+__global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl, long long gstep) {
   // networks b0 .. b0+nbl-1 (the whole batch, or the share of one sub-stream)
   long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n_j = (long long)nbl * nd.nj, n_l = (long long)nbl * nd.nl;
@@ -403,15 +446,40 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl) {
       ba = b * nd.na + nd.leaf_art[l];
     }
     const Vessel ves = nd.ves[ba];
-    cudaGridDependencySynchronize();
-    // only now may the artery kernel of THIS step start its prologue: it reads the
-    // Un that the previous artery kernel has just finished writing
-    cudaTriggerProgrammaticLaunchCompletion();
-    if (nd.stop_on_fail && *nd.fail_step != AF_NO_FAIL) return;     // an artery solve failed: the run is over
+    const bool dataflow = nd.dataflow && gstep >= 0;
+    if (dataflow) {
+      // Dataflow: no grid-wide wait.  The artery kernel of this step may become resident right away
+      // (its CTAs wait for their own flags); this task waits for the arteries whose Un it reads --
+      // lane v of a junction for vessel v, a leaf for its artery -- to have completed step gstep - 1.
+      cudaTriggerProgrammaticLaunchCompletion();
+      if (is_junction || is_leaf) {
+        if ((threadIdx.x & 31) < (is_junction ? 3 : 1)) wait_flag(&nd.f_art[ba], (unsigned)gstep, nd.fail_step, &nd.flags[b]);
+        __syncwarp();
+      }
+    } else {
+      cudaGridDependencySynchronize();
+      // only now may the artery kernel of THIS step start its prologue: it reads the
+      // Un that the previous artery kernel has just finished writing
+      cudaTriggerProgrammaticLaunchCompletion();
+    }
+    const long long flag_step = dataflow ? gstep : -1;
+    if (nd.stop_on_fail && *(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) {
+      // an artery solve failed: the run is over -- but nobody may be left waiting for this task
+      if (dataflow && (threadIdx.x & 31) == 0) {
+        if (is_junction) {
+          st_release_u32(&nd.f_out[b * nd.na + ia[0]], (unsigned)(gstep + 1));
+          st_release_u32(&nd.f_in[b * nd.na + ia[1]], (unsigned)(gstep + 1));
+          st_release_u32(&nd.f_in[b * nd.na + ia[2]], (unsigned)(gstep + 1));
+        } else if (is_leaf) {
+          st_release_u32(&nd.f_out[ba], (unsigned)(gstep + 1));
+        }
+      }
+      return;
+    }
     if (is_junction)
-      junction_task_warp(nd, cur, b, j, ia, ves, log_slot);
+      junction_task_warp(nd, cur, b, j, ia, ves, log_slot, flag_step);
     else if (is_leaf)
-      leaf_solve_warp(nd, cur, b, l, ba, ves, log_slot);
+      leaf_solve_warp(nd, cur, b, l, ba, ves, log_slot, flag_step);
   } else {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
@@ -643,9 +711,19 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   // kernel between them waits for it before it triggers), so its fail_step is visible here.
   // (not in the one-warp kernel, whose register budget it would break: there the boundary kernel's
   // early return and the host's polling end the run)
-  if (T > 32 && nd.stop_on_fail && *nd.fail_step != AF_NO_FAIL) return;
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
+  const bool dataflow = T > 32 && !FUSED && nd.dataflow && gstep >= 0;
+  if (T > 32 && nd.stop_on_fail && *(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) {
+    if (dataflow && tid == 0) st_release_u32(&nd.f_art[ba], (unsigned)(gstep + 1));   // nobody may be left waiting
+    return;
+  }
+  if (dataflow) {
+    // this artery's own previous step (another CTA of the previous artery kernel) must be complete before
+    // its Un is read; in the plain scheme the boundary kernel's grid-wide wait guarantees that
+    if (tid == 0) wait_flag(&nd.f_art[ba], (unsigned)gstep, nd.fail_step, &nd.flags[b]);
+    __syncthreads();
+  }
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
   {
@@ -760,7 +838,16 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       // first pass) only needs the previous artery kernel's output and has been
       // running under the boundary kernel of this step (programmatic dependent
       // launch); the Dirichlet data it writes is needed from here on.
-      cudaGridDependencySynchronize();
+      if (dataflow) {
+        // the Dirichlet data of exactly this artery's two ends (the barrier below publishes the acquire)
+        if (tid == 0) {
+          if (!c.root) wait_flag(&nd.f_in[ba], (unsigned)(gstep + 1), nd.fail_step, &nd.flags[b]);
+          wait_flag(&nd.f_out[ba], (unsigned)(gstep + 1), nd.fail_step, &nd.flags[b]);
+        }
+        __syncthreads();
+      } else {
+        cudaGridDependencySynchronize();
+      }
       // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
       c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
       c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
@@ -850,6 +937,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
         if (i0 + k < np) { gA[i0 + k] = sA[k * T + tid]; gq[i0 + k] = sq[k * T + tid]; }
     }
   }
+  if (dataflow) __syncthreads();        // every thread's part of Un is written before thread 0 releases it
   if (tid == 0) {
     nd.art_its[ba] = it;
     if (log_slot >= 0) nd.log_art[(size_t)log_slot * nd.nb * nd.na + ba] = it;
@@ -858,7 +946,16 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       atomicOr(&nd.flags[b], fl);
       if (fl & AF_FLAG_ARTERY_NOCONV) atomicMin(nd.fail_step, (unsigned long long)(gstep >= 0 ? gstep : 0));
     }
+    if (dataflow) {
+      __threadfence();
+      st_release_u32(&nd.f_art[ba], (unsigned)(gstep + 1));
+    }
   }
+}
+
+__global__ void k_set_flags(unsigned* p, int n, unsigned v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -1374,7 +1471,7 @@ static cudaError_t run_artery(const af_net* n, int ba0, int count, int inlet_ind
 }
 
 static cudaError_t run_boundary(const af_net* n, int log_slot, int b0 = 0, int nbl = -1, cudaStream_t stream = nullptr,
-                                bool in_loop = false) {
+                                bool in_loop = false, long long gstep = -1, bool allow_early = true) {
   NetDev nd = n->nd;
   if (!in_loop) nd.stop_on_fail = 0;
   if (nbl < 0) nbl = n->nd.nb;
@@ -1390,12 +1487,12 @@ static cudaError_t run_boundary(const af_net* n, int log_slot, int b0 = 0, int n
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = n->pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (n->pdl && allow_early) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (n->boundary_lanes == 32)
-    return cudaLaunchKernelEx(&cfg, k_boundary<true>, nd, n->cur, log_slot, b0, nbl);
-  return cudaLaunchKernelEx(&cfg, k_boundary<false>, nd, n->cur, log_slot, b0, nbl);
+    return cudaLaunchKernelEx(&cfg, k_boundary<true>, nd, n->cur, log_slot, b0, nbl, gstep);
+  return cudaLaunchKernelEx(&cfg, k_boundary<false>, nd, n->cur, log_slot, b0, nbl, gstep);
 }
 
 extern "C" int af_net_create(const af_desc* d, af_net** out) {
@@ -1521,6 +1618,9 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   AF_TRY(n->dalloc(&nd.totals, 3));
   AF_TRY(n->dalloc(&nd.flags, nd.nb));
   AF_TRY(n->dalloc(&nd.fail_step, 1));
+  AF_TRY(n->dalloc(&nd.f_art, nba));
+  AF_TRY(n->dalloc(&nd.f_in, nba));
+  AF_TRY(n->dalloc(&nd.f_out, nba));
   AF_TRY(n->dalloc(&n->scratch, 4096));
   cudaMemsetAsync(nd.art_its, 0, nba * sizeof(int), n->stream);
   cudaMemsetAsync(nd.j_solves, 0, (size_t)nd.nb * nd.nj * sizeof(int) + 0, n->stream);
@@ -1554,6 +1654,10 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
     if ((a != 0 && art_jin[a] < 0) || (art_leaf[a] < 0 && art_jout[a] < 0)) n->fused = false;
   if (const char* env = getenv("AF_NO_FUSE")) if (atoi(env)) n->fused = false;
   if (const char* env = getenv("AF_NO_PDL")) if (atoi(env)) n->pdl = false;
+  // dataflow flags instead of grid-wide waits: single networks on the warp-per-task boundary kernel and a
+  // multi-warp artery kernel (AF_NO_DATAFLOW=1: the plain programmatic-dependent-launch chain)
+  nd.dataflow = (nd.nb == 1 && n->boundary_lanes == 32 && n->artery_threads >= 64 && !n->fused) ? 1 : 0;
+  if (const char* env = getenv("AF_NO_DATAFLOW")) if (atoi(env)) nd.dataflow = 0;
   // sub-streams for ensembles: every share must still fill the machine (148 SMs x 16 one-warp CTAs) twice over
   if (n->boundary_lanes == 1) {
     const long long ctas = (long long)nd.nb * nd.na, fill = 2LL * 148 * AF_T32_BLOCKS;
@@ -1760,6 +1864,14 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
   if (n_first < 0 || n_steps < 0) return fail(AF_EINVAL, "negative step range");
   if (n->n_pending) return fail(AF_ESTATE, "arteries with a pending solve: call af_artery_update first");
   const int Nt = n->nd.Nt;
+  if (n->nd.dataflow && n_steps > 0) {
+    // the flags count time steps: everything up to step n_first - 1 is complete, nothing of step n_first is
+    const int nba = n->nd.nb * n->nd.na;
+    k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_art, nba, (unsigned)n_first);
+    k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_in, nba, (unsigned)n_first);
+    k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_out, nba, (unsigned)n_first);
+    AF_CUDA(cudaGetLastError());
+  }
   const bool split = n->n_sub > 1 && n_steps > 0;
   if (split && (rc = fork_subs(n))) return rc;
   for (int64_t g = n_first; g < n_first + n_steps; ++g) {
@@ -1796,11 +1908,14 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     } else if (split) {
       for (int k = 0; k < n->n_sub; ++k) {
         const int b0 = (int)((long long)n->nd.nb * k / n->n_sub), b1 = (int)((long long)n->nd.nb * (k + 1) / n->n_sub);
-        AF_CUDA(run_boundary(n, log_slot, b0, b1 - b0, n->sub[k], true));
+        AF_CUDA(run_boundary(n, log_slot, b0, b1 - b0, n->sub[k], true, g));
         AF_CUDA(run_artery(n, b0 * n->nd.na, (b1 - b0) * n->nd.na, inlet, log_slot, false, n->sub[k], g));
       }
     } else {
-      AF_CUDA(run_boundary(n, log_slot, 0, -1, nullptr, true));
+      // dataflow: the first boundary kernel of a call starts in plain stream order, after the kernels that
+      // reset the flags have completed (a dependent launch that never calls cudaGridDependencySynchronize
+      // has no visibility guarantee for what its predecessor wrote)
+      AF_CUDA(run_boundary(n, log_slot, 0, -1, nullptr, true, g, !(n->nd.dataflow && g == n_first)));
       AF_CUDA(run_artery(n, 0, n->nd.nb * n->nd.na, inlet, log_slot, false, nullptr, g));
     }
     n->cur ^= 1;

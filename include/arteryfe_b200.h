@@ -42,6 +42,7 @@ extern "C" {
 #define AF_FLAG_PICARD_KMAX 4u    /* Windkessel Picard ran all k_max iterations (an:411, silent) */
 #define AF_FLAG_NONFINITE 8u      /* NaN/Inf in a residual norm */
 #define AF_FLAG_SINGULAR 16u      /* singular 18x18: the perturbation path an:703-708 was taken */
+#define AF_FLAG_SYNC_TIMEOUT 64u  /* a dataflow wait between kernels of the time loop gave up (never expected) */
 #define AF_FLAG_PICARD_CYCLE 32u  /* Windkessel Picard ended in a round-off limit cycle: the reference runs all k_max
                                      iterations there (an:411); the kernel returns the same value without them */
 

@@ -133,9 +133,11 @@ for name, p, steps in (('c1', af.ParamParser('tests/golden/golden_c1.cfg'), 120)
     an = af.ArteryNetwork(p)
     an.define_x()
     an._dev.set_counter_log(steps)
-    an._dev.step(0, steps)
+    an._dev.step(0, steps // 2)                   # two calls: the dataflow flags are re-based per call
+    an._dev.step(steps // 2, steps - steps // 2)
     A, q = an._dev.get_state()
     a, j, pi = an._dev.fetch_counter_log()
+    assert int(an._dev.get_flags()[0]) & 64 == 0  # AF_FLAG_SYNC_TIMEOUT
     out.update({name + '_A': A, name + '_q': q, name + '_x': an._dev.get_junction_x(), name + '_bc': an._dev.get_bc(),
                 name + '_dex': an._dev.get_dex(), name + '_a': a, name + '_j': j, name + '_p': pi})
 ens = en.EnsembleNetwork(tree_param(4, Nx=100, Nt=2000), 700, first_index=5)
@@ -149,20 +151,22 @@ np.savez(sys.argv[1], **out)
 
 
 def test_plain_stream_order_equals_programmatic_dependent_launch(tmp_path):
-    """AF_NO_PDL=1 (plain stream order between the two kernels of a step) against the default
-    programmatic dependent launch: state, junction unknowns, Dirichlet data, dex and every counter
+    """The default scheduling (programmatic dependent launch + per-artery / per-junction dataflow flags
+    on multi-warp single networks) against AF_NO_DATAFLOW=1 (dependent launch with grid-wide waits) and
+    AF_NO_PDL=1 (plain stream order between the two kernels of a step): state, junction unknowns, Dirichlet data, dex and every counter
     bitwise equal on the demo bifurcation, the order-3 tree, a short run of the order-8 tree and a
     700-member ensemble.  Guards the 'only constants before the grid-dependency wait' rule of
     k_boundary / k_artery (af_kernels.cu)."""
     script = tmp_path / 'pdl_worker.py'
     script.write_text(PDL_WORKER % {'root': ROOT})
     outs = []
-    for tag, env in (('pdl', {}), ('plain', {'AF_NO_PDL': '1'})):
+    for tag, env in (('default', {}), ('no_dataflow', {'AF_NO_DATAFLOW': '1'}), ('plain', {'AF_NO_PDL': '1'})):
         path = str(tmp_path / (tag + '.npz'))
         r = subprocess.run([sys.executable, str(script), path], env=dict(os.environ, **env), capture_output=True,
                            text=True, timeout=900)
         assert r.returncode == 0, r.stdout + r.stderr
         outs.append(np.load(path))
-    assert set(outs[0].files) == set(outs[1].files)
-    for key in outs[0].files:
-        np.testing.assert_array_equal(outs[0][key], outs[1][key], err_msg=key)
+    for other in outs[1:]:
+        assert set(outs[0].files) == set(other.files)
+        for key in outs[0].files:
+            np.testing.assert_array_equal(outs[0][key], other[key], err_msg=key)
