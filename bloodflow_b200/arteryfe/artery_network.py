@@ -10,6 +10,7 @@ same device code the time loop uses, one call at a time.
 """
 import configparser
 import os
+import weakref
 
 import copy
 
@@ -48,7 +49,9 @@ class _Arteries(object):
     255 Python objects it may never touch."""
 
     def __init__(self, net):
-        self._net, self._made = net, {}
+        # a weak reference: the network must die by reference count (no cycle), so that its device and
+        # pinned blocks return to the library's caches as soon as the caller drops it
+        self._net, self._made = weakref.proxy(net), {}
 
     def __len__(self):
         return self._net.N

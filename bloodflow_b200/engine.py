@@ -87,6 +87,7 @@ class DeviceNetwork(object):
         if getattr(self, '_h', None):
             lib.af_net_destroy(self._h)
             self._h = None
+        self._host_store = None
 
     def __del__(self):
         try:
