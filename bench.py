@@ -329,21 +329,21 @@ def run_c5(args, rank, local_rank, world, torch, dist, sampler):
         c2.record(stream)
     torch.cuda.synchronize()
     flags = dev.get_flags()
-    bad = torch.tensor([int(np.count_nonzero(flags & np.uint32(1 | 8))), int(np.bitwise_or.reduce(flags))],
-                       dtype=torch.int64, device='cuda')
-    tot = torch.from_numpy(dev.get_totals().astype(np.int64)).cuda()
+    # one SUM all-reduce: members with a failure, the three iteration totals, and per status bit the number of
+    # members that have it set (NCCL has no bitwise OR)
+    bits = [int(np.count_nonzero(flags & np.uint32(1 << k))) for k in range(8)]
+    packed_i = torch.tensor([int(np.count_nonzero(flags & np.uint32(1 | 8)))] + [int(v) for v in dev.get_totals()] + bits,
+                            dtype=torch.int64, device='cuda')
     if world > 1:
-        both = torch.cat([bad[:1], tot])
-        dist.all_reduce(both, op=dist.ReduceOp.SUM)
-        flag_or = bad[1:].clone()
-        dist.all_reduce(flag_or, op=dist.ReduceOp.BOR)
-        bad = torch.cat([both[:1], flag_or])
-        tot = both[1:]
+        dist.all_reduce(packed_i, op=dist.ReduceOp.SUM)
+    packed_i = packed_i.cpu().numpy()
+    n_flagged, tot, bits = int(packed_i[0]), packed_i[1:4], packed_i[4:]
+    flags_or = int(sum(1 << k for k in range(8) if bits[k] > 0))
     if rank != 0:
         return None
     peaks, peak_kind = measured_peaks()
     value = nodes_total * steps / (ms_total * 1e-3)
-    its = float(tot[0].item()) / (float(total) * dev.na * steps)
+    its = float(tot[0]) / (float(total) * dev.na * steps)
     fl = flops_per_vertex_step(its)
     cap = committed_capture("k_artery<32>")
     peak_tf = fp64_peak(local_rank)
@@ -354,7 +354,10 @@ def run_c5(args, rank, local_rank, world, torch, dist, sampler):
         "members_total": total, "members_per_gpu": M, "n_gpus": world, "steps": steps, "scaling": "strong",
         "value": value, "unit": UNIT, "ms_per_step": ms_total / steps, "seconds": ms_total * 1e-3,
         "cycles_per_sec_all_networks": total * (steps / C5_NT) / (ms_total * 1e-3),
-        "flags_or": int(bad[1].item()), "flagged_members": int(bad[0].item()),
+        "flags_or": flags_or, "flagged_members": n_flagged,
+        "members_per_status_bit": {"artery_noconv": int(bits[0]), "junction_kmax": int(bits[1]), "picard_kmax": int(bits[2]),
+                                   "nonfinite": int(bits[3]), "singular": int(bits[4]), "picard_cycle": int(bits[5]),
+                                   "sync_timeout": int(bits[6])},
         "flagged_members_meaning": "members with an artery Newton failure or a non-finite residual (must be 0)",
         "newton_its_per_artery_step": its,
         "collective": {"kind": "one all_gather of the packed moments [5, snapshots, leaves] per rank + fold kernel",
