@@ -688,6 +688,35 @@ __device__ __forceinline__ double rows_from_smem(const ArteryCtx& c, const doubl
   return part;
 }
 
+// The convergence check after a Newton update needs the residual only (DOLFIN tests ||R|| after every
+// update, [3P] NewtonSolver).  Lean pass: the flux / source sums of the four own cells stay in registers,
+// one double per thread (the right-vertex sum of its last cell) crosses to the next thread, no Jacobian,
+// nothing parked.  Returns the thread's share of ||R||^2.  `ex` is a T-double exchange buffer.
+template <int T>
+__device__ __forceinline__ double residual_pass(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
+                                                const double* sA, const double* sq, double* ex, double* EA,
+                                                double* Eq) {
+  const int tid = threadIdx.x, i0 = 4 * tid;
+  CellInt cell[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cell[k] = artery_cell<T, false>(c, ccu, tab, S, sA, sq, i0 + k);
+  ex[tid] = cell[3].Gr;
+  cta_sync<T>();
+  CellInt left;
+  left.Gr = tid > 0 ? ex[tid - 1] : 0.0;
+  double part = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + k;
+    const int jm = vix<T>(i > 0 ? i - 1 : i), j0 = vix<T>(i), jp = vix<T>(i < 4 * T - 1 ? i + 1 : i);
+    Row row;
+    const CellInt& lf = k == 0 ? left : cell[k > 0 ? k - 1 : 0];      // the cell to the left of vertex i
+    build_row<false>(c, i, false, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], lf, cell[k], EA[k], Eq[k], row);
+    part += row.r[0] * row.r[0] + row.r[1] * row.r[1];
+  }
+  return part;
+}
+
 template <int T, bool FUSED>
 __global__ void __launch_bounds__(T, (T == 32 ? AF_T32_BLOCKS : (T <= 256 ? 512 / T : 1)))
 k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long gstep) {
@@ -824,13 +853,18 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   int it = 0;
   double r_first = 0.0;
   uint32_t fl = 0;
+  // How many linear solves this artery needed in the previous time step: the convergence test after
+  // solve number `expect` (and later ones) is done by the lean residual-only pass at the bottom of the
+  // loop -- it will most likely say "converged", and a full pass there would assemble a Jacobian and
+  // eliminate half the rows for nothing.  Before that the test is part of the full pass that the next
+  // solve needs anyway.  The prediction only selects which code computes ||R||; the iterates, the tests
+  // and the count are those of [3P] NewtonSolver either way.
+  const int prev_its = nd.art_its[ba];
+  const int expect = prev_its > 1 ? prev_its : 1;
+  bool test_here = true;
   for (;;) {
     const bool first = (it == 0);
-    // ---- cells -> shared memory, then rows and level 0 of the reduction ------------
-    // The Jacobian is always assembled with the residual: a residual-only variant
-    // for the (usually converged) last pass was measured slower -- the second copy
-    // of the assembly code costs more instruction-cache misses than the skipped
-    // derivative terms save (tree 59.3 -> 57.7 us/step, ensemble +8 % without it).
+    // ---- full pass: cells -> shared memory, then rows (residual + Jacobian) and level 0 of the reduction
     Row rb, rd;
     cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
     if (!FUSED && first) {
@@ -859,12 +893,14 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     cta_sync<T>();
     double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
     const double r2 = block_sum<T>(part, red);    // its two barriers also publish pa/pc
-    const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
-    // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ------------------
-    if (first) r_first = r;
-    if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
-    if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
-    if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
+    if (test_here) {
+      // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ----------
+      const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
+      if (first) r_first = r;
+      if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
+      if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
+      if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
+    }
     // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------
     if (tid + 1 < T) {
       Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
@@ -920,6 +956,16 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     }
     cta_sync<T>();
     ++it;
+    // ---- convergence test after the update ([3P] NewtonSolver::converged), residual only ----------
+    test_here = it < expect;          // too early to expect convergence: the next full pass tests
+    if (!test_here) {
+      const double part2 = residual_pass<T>(c, ccu, tab, S, sA, sq, Lo, EA, Eq);
+      const double q2 = block_sum<T>(part2, red);
+      const double r = q2 > 0.0 ? af_sqrt_pos(q2) : q2;
+      if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
+      if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
+      if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
+    }
   }
   // update_solution (ar:247-251): Un <- U, into the other buffer
   {
