@@ -120,21 +120,21 @@ class ArteryNetwork(object):
 
         self.check_geometry()
 
-        # an:87-118 -- which vessels exist, root / parent / daughter / leaf classification
+        # an:87-118 -- which vessels exist, root / parent / daughter / leaf classification (the reference's
+        # loop over the heap indices, for all vessels at once)
         self._exists = np.asarray(self.nondim['Ru']) != 0
         self.arteries = _Arteries(self)
-        self.range_parent_arteries = [0]
-        self.range_daughter_arteries = []
-        self.range_leaf_arteries = []
-        for i in range(1, self.N):
-            if not self._exists[i]:
-                continue
-            self.range_daughter_arteries.append(i)
-            d1, d2 = self.daughter_arteries(i)
-            if d1 is None and d2 is None:
-                self.range_leaf_arteries.append(i)
-            else:
-                self.range_parent_arteries.append(i)
+        heap = np.arange(self.N)
+        has = np.zeros((2, self.N), dtype=bool)
+        for s in (0, 1):
+            k = 2 * heap + 1 + s
+            ok = k <= self.N - 1
+            has[s, ok] = self._exists[k[ok]]
+        self._has_daughter = has
+        body = self._exists & (heap >= 1)
+        self.range_daughter_arteries = heap[body].tolist()
+        self.range_leaf_arteries = heap[body & ~has[0] & ~has[1]].tolist()
+        self.range_parent_arteries = [0] + heap[body & (has[0] | has[1])].tolist()
         self._leaf_slot = {i: j for j, i in enumerate(self.range_leaf_arteries)}
 
         self._dev = None
@@ -165,17 +165,19 @@ class ArteryNetwork(object):
         lo = hi = 0
         for level in range(order):
             last_generation = not (2 ** (level + 1) - 1 < len(Rd))
-            for p in range(lo, hi):
-                d1, d2 = 2 * p + 1, 2 * p + 2
-                Ru[d1] = alpha * Ru[p] * Ru[d1]
-                Ru[d2] = max(0, alpha * Ru[p]) * Ru[d2]
-                if last_generation:
-                    Rd[d1] = Rd[d2] = R_term
-                else:
-                    Rd[d1] = alpha * Rd[p] * Rd[d1]
-                    Rd[d2] = max(0, alpha * Rd[p]) * Rd[d2]
-                lengths[d1] = L * Ru[d1]
-                lengths[d2] = L * Ru[d2] - 0.01
+            # the reference's loop over the parents p of this generation, all of them at once (parents and
+            # daughters of one generation are disjoint index ranges, so the order within it does not matter)
+            p = np.arange(lo, hi)
+            d1, d2 = 2 * p + 1, 2 * p + 2
+            Ru[d1] = alpha * Ru[p] * Ru[d1]
+            Ru[d2] = np.maximum(0, alpha * Ru[p]) * Ru[d2]
+            if last_generation:
+                Rd[d1] = Rd[d2] = R_term
+            else:
+                Rd[d1] = alpha * Rd[p] * Rd[d1]
+                Rd[d2] = np.maximum(0, alpha * Rd[p]) * Rd[d2]
+            lengths[d1] = L * Ru[d1]
+            lengths[d2] = L * Ru[d2] - 0.01
             lo += int(2 ** (level - 1))
             hi += int(2 ** level)
         return Ru, Rd, lengths
@@ -225,22 +227,33 @@ class ArteryNetwork(object):
         """artery_network.py:258-279: initial flows (root q_ins[0]; daughters
         split by inlet rest areas), then the device-resident state."""
         idx = self._idx
-        self._compact = {int(i): k for k, i in enumerate(idx)}
+        self._compact = {i: k for k, i in enumerate(idx.tolist())}
+        compact = np.full(self.N, -1, dtype=np.int64)
+        compact[idx] = np.arange(len(idx))
         g = self._geom
         # Artery.A0(0) of every vessel: pi * (Ru * (Rd/Ru)**(0/L))**2, the facade's expressions (ar:110-112)
-        A0_in = dict(zip(idx.tolist(), (np.pi * np.power(g['Ru'] * np.power(g['Rd'] / g['Ru'], 0 / g['L']), 2)).tolist()))
-        q0 = {0: self.q_ins[0]}
-        for i in self.range_daughter_arteries:
-            a0, s0 = A0_in[i], A0_in[self.sister_artery(i)]
-            q0[i] = a0 / (a0 + s0) * q0[self.parent_artery(i)]
-        junctions = []
-        for ip in self.range_parent_arteries:
-            i1, i2 = self.daughter_arteries(ip)
-            if i1 is None or i2 is None:
-                raise ValueError("artery %d has exactly one daughter; a parent needs two "
-                                 "(artery_network.py:111-118)" % ip)
-            junctions.append([self._compact[ip], self._compact[i1], self._compact[i2]])
-        leaves = [self._compact[i] for i in self.range_leaf_arteries]
+        A0_in = np.ones(self.N)
+        A0_in[idx] = np.pi * np.power(g['Ru'] * np.power(g['Rd'] / g['Ru'], 0 / g['L']), 2)
+        # an:262-276, one generation at a time (a daughter's share needs its parent's flow)
+        q0_all = np.zeros(self.N)
+        q0_all[0] = self.q_ins[0]
+        heap = np.arange(self.N)
+        sister = np.where(heap % 2 == 1, heap + 1, heap - 1)
+        sister[0] = 0
+        for level in range(1, self.nondim['order']):
+            i = heap[2 ** level - 1:2 ** (level + 1) - 1]
+            i = i[self._exists[i]]
+            q0_all[i] = A0_in[i] / (A0_in[i] + A0_in[sister[i]]) * q0_all[(i - 1) // 2]
+        q0 = dict(zip(idx.tolist(), q0_all[idx].tolist()))
+        parents = np.asarray(self.range_parent_arteries, dtype=np.int64)
+        has = self._has_daughter[:, parents]
+        if not np.all(has[0] & has[1]):
+            ip = int(parents[np.flatnonzero(~(has[0] & has[1]))[0]])
+            raise ValueError("artery %d has exactly one daughter; a parent needs two "
+                             "(artery_network.py:111-118)" % ip)
+        junctions = np.stack([compact[parents], compact[2 * parents + 1], compact[2 * parents + 2]], axis=1)
+        leaves = compact[np.asarray(self.range_leaf_arteries, dtype=np.int64)]
+        self._q0_compact = q0_all[idx]
         self._q0 = q0
         self._description = self.describe(junctions, leaves, q0)
         if self._dev is not None:
@@ -262,7 +275,7 @@ class ArteryNetwork(object):
             Nx=self.geo['Nx'], Nt=self.geo['Nt'], theta=self.sol['theta'], dt=self.dt,
             junctions=np.array(junctions, dtype=np.int32).reshape(-1, 3), leaves=np.array(leaves, dtype=np.int32),
             k1=nd['k1'], k2=nd['k2'], k3=nd['k3'], rho=nd['rho'], Re=nd['Re'], db=self._db, p0=nd['p0'],
-            Ru=g['Ru'], Rd=g['Rd'], L=g['L'], q0=np.array([q0[int(i)] for i in self._idx]),
+            Ru=g['Ru'], Rd=g['Rd'], L=g['L'], q0=self._q0_compact.copy(),
             R1=R1 * self.wk_scale[0], R2=R2 * self.wk_scale[1], CT=CT,
             q_ins=self.q_ins)
 

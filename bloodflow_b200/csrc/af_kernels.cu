@@ -33,11 +33,19 @@ using namespace af;
 #define AF_NO_FAIL 0xffffffffffffffffull
 
 // ---- release / acquire flags in global memory (the semaphore pattern: one thread of the producer
-// releases after a CTA / warp barrier, one thread of the consumer acquires before one) ----
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+// releases after a CTA / warp barrier, one thread of the consumer acquires before one).  In the PTX
+// memory model a release is "fence.acq_rel ; st.relaxed" and an acquire "ld.relaxed ; fence.acq_rel";
+// the fences are spelled out so that a producer with several flags pays for ONE (the junction releases
+// three artery ends), a consumer spins on plain relaxed loads, and nobody issues the heavier
+// sequentially-consistent fence of __threadfence() (ncu: `membar` was the 4th stall reason of k_boundary).
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -48,12 +56,13 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 #define AF_FLAG_SYNC_TIMEOUT 64u
 __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned want, const unsigned long long* fail_step,
                                           uint32_t* status) {
-  for (unsigned spins = 0; (int)(ld_acquire_u32(p) - want) < 0; ++spins) {
+  for (unsigned spins = 0; (int)(ld_relaxed_u32(p) - want) < 0; ++spins) {
     if ((spins & 63u) == 63u) {
       if (*(volatile const unsigned long long*)fail_step != AF_NO_FAIL) return;
       if (spins > (1u << 23)) { atomicOr(status, AF_FLAG_SYNC_TIMEOUT); return; }
     }
   }
+  fence_acq_rel_gpu();
 }
 
 // ---------------------------------------------------------------------------
@@ -204,16 +213,17 @@ __device__ __forceinline__ void junction_finish(const NetDev& nd, int b, int j, 
   nd.bc[b1 * 4 + 0] = x[12]; nd.bc[b1 * 4 + 1] = x[3];
   nd.bc[b2 * 4 + 0] = x[15]; nd.bc[b2 * 4 + 1] = x[6];
   nd.dex[bp] = dex;    // the value a non-leaf vessel holds after set_bcs
+  if (flag_step >= 0) {        // dataflow: the three artery ends may go on (one thread wrote everything above)
+    fence_acq_rel_gpu();
+    st_relaxed_u32(&nd.f_out[bp], (unsigned)(flag_step + 1));
+    st_relaxed_u32(&nd.f_in[b1], (unsigned)(flag_step + 1));
+    st_relaxed_u32(&nd.f_in[b2], (unsigned)(flag_step + 1));
+  }
+  // bookkeeping nobody waits for: after the release, off the critical path of the step
   nd.j_solves[b * nd.nj + j] = solves;
   if (log_slot >= 0) nd.log_j[(size_t)log_slot * nd.nb * nd.nj + b * nd.nj + j] = solves;
   atomicAdd(&nd.totals[1], (unsigned long long)solves);
   if (fl) atomicOr(&nd.flags[b], fl);
-  if (flag_step >= 0) {        // dataflow: the three artery ends may go on (one thread wrote everything above)
-    __threadfence();
-    st_release_u32(&nd.f_out[bp], (unsigned)(flag_step + 1));
-    st_release_u32(&nd.f_in[b1], (unsigned)(flag_step + 1));
-    st_release_u32(&nd.f_in[b2], (unsigned)(flag_step + 1));
-  }
 }
 
 // verbatim dense path (reference formulas, 18x18 LU): owns the singular branch an:703-708
@@ -402,14 +412,11 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
   nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
   nd.dex[ba] = r.dex;
+  if (flag_step >= 0) st_release_u32(&nd.f_out[ba], (unsigned)(flag_step + 1));
   nd.picard_its[b * nd.nl + l] = r.its;
   if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
   atomicAdd(&nd.totals[2], (unsigned long long)r.its);
   if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)(r.cycle ? AF_FLAG_PICARD_CYCLE : AF_FLAG_PICARD_KMAX));
-  if (flag_step >= 0) {
-    __threadfence();
-    st_release_u32(&nd.f_out[ba], (unsigned)(flag_step + 1));
-  }
   return r;
 }
 
@@ -986,15 +993,14 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   if (dataflow) __syncthreads();        // every thread's part of Un is written before thread 0 releases it
   if (tid == 0) {
     nd.art_its[ba] = it;
+    // the release is cumulative over what the other threads wrote before the barrier above
+    if (dataflow) st_release_u32(&nd.f_art[ba], (unsigned)(gstep + 1));
+    // bookkeeping nobody waits for: after the release, off the critical path of the step
     if (log_slot >= 0) nd.log_art[(size_t)log_slot * nd.nb * nd.na + ba] = it;
     atomicAdd(&nd.totals[0], (unsigned long long)it);
     if (fl) {
       atomicOr(&nd.flags[b], fl);
       if (fl & AF_FLAG_ARTERY_NOCONV) atomicMin(nd.fail_step, (unsigned long long)(gstep >= 0 ? gstep : 0));
-    }
-    if (dataflow) {
-      __threadfence();
-      st_release_u32(&nd.f_art[ba], (unsigned)(gstep + 1));
     }
   }
 }
@@ -1363,7 +1369,8 @@ struct af_net {
   // word; once it shows a failed artery solve af_net_step stops enqueuing (the launches already queued
   // return at once, see k_artery)
   static const int kPoll = 64;
-  unsigned long long* fail_h = nullptr;   // pinned
+  static const size_t kFailBytes = 64;
+  unsigned long long* fail_h = nullptr;   // pinned (from / back to the host block cache)
   cudaEvent_t fail_ev = nullptr;
   bool fail_poll_pending = false;
   bool failed = false;
@@ -1372,14 +1379,64 @@ struct af_net {
   std::vector<uint8_t> pending;   // per artery: U computed by af_artery_solve, not yet assigned to Un
   int n_pending = 0;
 
+  // Set-up arena: while af_net_create runs, small blocks (topology, parameters, holders, counters) are
+  // carved out of ONE device block, and what is uploaded into them is first written to a pinned mirror of
+  // it; arena_flush() then moves zeros and data with a single copy.  A network description is ~40 small
+  // arrays: one allocation + one copy instead of ~100 driver calls (0.3 ms of every ArteryNetwork(param)).
+  static const size_t kArenaBytes = (size_t)1 << 20, kArenaBlockMax = (size_t)128 << 10;
+  char* arena_d = nullptr;
+  char* arena_h = nullptr;        // pinned mirror, only alive during af_net_create
+  size_t arena_off = 0;
+  bool arena_open = false;
+  int arena_begin() {
+    if (cache().host_cap == 0) return AF_OK;     // caches disabled (AF_CACHE_MB=0): no pinned mirror per network
+    void* q = nullptr;
+    {
+      double* blk = nullptr;
+      int rc = dalloc(&blk, kArenaBytes / sizeof(double), /*clear=*/false);
+      if (rc) return rc;
+      q = blk;
+    }
+    arena_h = (char*)cache().take_host(kArenaBytes);
+    if (!arena_h && cudaHostAlloc((void**)&arena_h, kArenaBytes, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      arena_h = nullptr;
+      return AF_OK;                // no mirror: every block takes the ordinary path
+    }
+    arena_d = (char*)q;
+    arena_off = 0;
+    arena_open = true;
+    return AF_OK;
+  }
+  // one copy for everything carved so far (zeros included); no further block comes from the arena
+  cudaError_t arena_flush() {
+    if (!arena_open) return cudaSuccess;
+    arena_open = false;
+    return arena_off ? cudaMemcpyAsync(arena_d, arena_h, arena_off, cudaMemcpyHostToDevice, stream) : cudaSuccess;
+  }
+  void arena_release_mirror() {    // after the stream has been synchronised
+    if (arena_h && !cache().give_host(kArenaBytes, arena_h)) cudaFreeHost(arena_h);
+    arena_h = nullptr;
+    arena_open = false;
+  }
+  bool in_arena(const void* p) const {
+    return arena_d && (const char*)p >= arena_d && (const char*)p < arena_d + kArenaBytes;
+  }
+
   template <typename Tp>
-  int dalloc(Tp** p, size_t n) {
+  int dalloc(Tp** p, size_t n, bool clear = true) {
     const size_t bytes = (((n ? n : 1) * sizeof(Tp)) + 511) & ~(size_t)511;
+    if (arena_open && bytes <= kArenaBlockMax && arena_off + bytes <= kArenaBytes) {
+      memset(arena_h + arena_off, 0, bytes);
+      *p = (Tp*)(arena_d + arena_off);
+      arena_off += bytes;
+      return AF_OK;
+    }
     void* q = cache().take_dev(device, bytes);
     if (q) {
       // a recycled block holds the previous owner's data: clear it (a memset at HBM speed is
       // far cheaper than the cudaMalloc it replaces)
-      cudaError_t e = cudaMemsetAsync(q, 0, bytes, stream);
+      cudaError_t e = clear ? cudaMemsetAsync(q, 0, bytes, stream) : cudaSuccess;
       if (e != cudaSuccess) {
         cudaFree(q);
         return fail(AF_ECUDA, std::string("cudaMemsetAsync of a recycled block: ") + cudaGetErrorString(e));
@@ -1432,6 +1489,10 @@ struct af_net {
   int upload(Tp** p, const Tp* h, size_t n) {
     int rc = dalloc(p, n);
     if (rc) return rc;
+    if (arena_open && in_arena(*p)) {
+      if (n) memcpy(arena_h + ((char*)*p - arena_d), h, n * sizeof(Tp));
+      return AF_OK;
+    }
     AF_CUDA(cudaMemcpyAsync(*p, h, n * sizeof(Tp), cudaMemcpyHostToDevice, stream));
     return AF_OK;
   }
@@ -1586,6 +1647,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   const size_t nba = (size_t)nd.nb * nd.na;
   int rc = AF_OK;
 #define AF_TRY(x) do { rc = (x); if (rc) { af_net_destroy(n); return rc; } } while (0)
+  AF_TRY(n->arena_begin());
   // topology
   std::vector<int> art_leaf(nd.na, -1);
   for (int l = 0; l < nd.nl; ++l) {
@@ -1668,6 +1730,10 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   AF_TRY(n->dalloc(&nd.f_in, nba));
   AF_TRY(n->dalloc(&nd.f_out, nba));
   AF_TRY(n->dalloc(&n->scratch, 4096));
+  {
+    cudaError_t ea = n->arena_flush();         // before the memsets below: the mirror holds zeros there
+    if (ea != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("set-up copy: ") + cudaGetErrorString(ea)); }
+  }
   cudaMemsetAsync(nd.art_its, 0, nba * sizeof(int), n->stream);
   cudaMemsetAsync(nd.j_solves, 0, (size_t)nd.nb * nd.nj * sizeof(int) + 0, n->stream);
   cudaMemsetAsync(nd.picard_its, 0, (size_t)nd.nb * nd.nl * sizeof(int) + 0, n->stream);
@@ -1676,7 +1742,9 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   cudaMemsetAsync(nd.fail_step, 0xff, sizeof(unsigned long long), n->stream);      // AF_NO_FAIL
   nd.stop_on_fail = (nd.nb == 1) ? 1 : 0;      // ensemble members are independent: a failed one is only flagged
   if (nd.stop_on_fail) {
-    cudaError_t ef = cudaHostAlloc((void**)&n->fail_h, sizeof(unsigned long long), cudaHostAllocDefault);
+    cudaError_t ef = cudaSuccess;
+    n->fail_h = (unsigned long long*)cache().take_host(af_net::kFailBytes);
+    if (!n->fail_h) ef = cudaHostAlloc((void**)&n->fail_h, af_net::kFailBytes, cudaHostAllocDefault);
     if (ef == cudaSuccess) ef = cudaEventCreateWithFlags(&n->fail_ev, cudaEventDisableTiming);
     if (ef != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("failure polling: ") + cudaGetErrorString(ef)); }
     *n->fail_h = AF_NO_FAIL;
@@ -1742,6 +1810,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   e = cudaStreamSynchronize(n->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("set-up kernels: ") + cudaGetErrorString(e)); }
+  n->arena_release_mirror();
 #undef AF_TRY
   *out = n;
   return AF_OK;
@@ -1758,7 +1827,8 @@ extern "C" void af_net_destroy(af_net* n) {
   }
   if (n->ev_fork) cudaEventDestroy(n->ev_fork);
   if (n->fail_ev) cudaEventDestroy(n->fail_ev);
-  if (n->fail_h) cudaFreeHost(n->fail_h);
+  if (n->fail_h && !cache().give_host(af_net::kFailBytes, n->fail_h)) cudaFreeHost(n->fail_h);
+  n->arena_release_mirror();
   for (auto& blk : n->allocs) af_net::release_block(n->device, blk.first, blk.second);
   for (cudaEvent_t ev : n->snap_event) cudaEventDestroy(ev);
   for (int k = 0; k < af_net::kRing; ++k) if (n->ring_done[k]) cudaEventDestroy(n->ring_done[k]);
@@ -2013,6 +2083,12 @@ extern "C" int af_artery_update(af_net* n, int32_t network, int32_t artery) {
   return AF_OK;
 }
 
+// member slices per snapshot of the moments reduction (>= 1024 members each)
+static int moments_slices(int nb) {
+  const int P = nb / 1024;
+  return P < 1 ? 1 : (P > 32 ? 32 : P);
+}
+
 extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t first_cycle, int32_t max_snapshots,
                                 int32_t fields) {
   int rc = check(n);
@@ -2033,6 +2109,15 @@ extern "C" int af_net_set_store(af_net* n, const uint8_t* step_mask, int32_t fir
     if (fields & AF_STORE_OUTLET_PRESSURE) {
       rc = n->dalloc(&n->s_outlet, (size_t)nd.nb * nd.nl * max_snapshots);
       if (rc) return rc;
+      // the moments of the stored outlet pressures (af_net_outlet_moments_d) are reduced into this buffer:
+      // allocated here, so that the statistics call after the loop only launches kernels
+      const size_t need = (size_t)(moments_slices(nd.nb) + 1) * 5 * max_snapshots * nd.nl;
+      if (need > n->moments_cap) {
+        n->dfree(&n->moments);
+        n->moments_cap = 0;
+        if ((rc = n->dalloc(&n->moments, need))) return rc;
+        n->moments_cap = need;
+      }
     }
     n->snap_cap = max_snapshots;
   }
@@ -2177,8 +2262,7 @@ extern "C" int af_net_outlet_moments_d(af_net* n, double** moments_d, int32_t* n
   const int ns = n->n_snap, n_out = ns * nd.nl;
   if (n_snapshots) *n_snapshots = ns;
   if (ns == 0) { *moments_d = nullptr; return AF_OK; }
-  int P = nd.nb / 1024;                          // member slices per snapshot (>= 1024 members each)
-  P = P < 1 ? 1 : (P > 32 ? 32 : P);
+  const int P = moments_slices(nd.nb);
   const size_t need = (size_t)(P + 1) * 5 * n_out;
   if (need > n->moments_cap) {
     AF_CUDA(cudaStreamSynchronize(n->stream));

@@ -170,3 +170,114 @@ def test_plain_stream_order_equals_programmatic_dependent_launch(tmp_path):
         assert set(outs[0].files) == set(other.files)
         for key in outs[0].files:
             np.testing.assert_array_equal(outs[0][key], other[key], err_msg=key)
+
+
+def _compare_with_c_oracle(dev, c, total, chunk, counts_exact=True):
+    """Step the device network and the C oracle side by side; state and junction unknowns to 1e-9 at
+    every checkpoint, artery Newton counts equal at every step, junction counts up to near-ties."""
+    dev.set_counter_log(total)
+    la, lj, done = [], [], 0
+    while done < total:
+        n = min(chunk, total - done)
+        dev.step(done, n)
+        failed, a_, j_ = c.step(done, n, nthreads=0, log=True)
+        assert failed == 0
+        la.append(a_)
+        lj.append(j_)
+        done += n
+        A, q = dev.get_state()
+        Ao, qo = c.state()
+        np.testing.assert_allclose(A[0], Ao, rtol=1e-9, err_msg='A at step %d' % done)
+        np.testing.assert_allclose(q[0], qo, rtol=1e-9, atol=1e-9 * np.abs(qo).max(), err_msg='q at step %d' % done)
+        np.testing.assert_allclose(dev.get_junction_x()[0], c.x(), rtol=1e-9)
+    art, jun, _ = dev.fetch_counter_log()
+    np.testing.assert_array_equal(art[:, 0], np.concatenate(la))
+    lj = np.concatenate(lj)
+    mism = np.count_nonzero(jun[:, 0] != lj)
+    if counts_exact:
+        assert mism == 0, mism
+    else:
+        assert mism <= 1e-3 * lj.size and np.abs(jun[:, 0] - lj).max() <= 1, mism
+    assert int(dev.get_flags()[0]) & (1 | 8) == 0
+    return mism
+
+
+def test_shipped_configs_full_horizon():
+    """BASELINE configs C1 and C2 at their stated size AND horizon against the C oracle: the shipped
+    demo_arterybranch.cfg (3 x 401 vertices) over its whole cardiac cycle of 4 000 steps with the documented
+    Windkessel factors (1, 1) (HEAD's factors diverge in step 0), and demo_arterybranch_geo.cfg
+    (+ R_term = 0.296, HEAD factors; 3 x 201 vertices) over all of its 4 cycles = 8 000 steps.  Neither
+    amplifies round-off (a 1e-13 perturbation stays below 4e-12 over the horizon, C oracle against itself)."""
+    import bloodflow_b200.arteryfe as af
+    from oracle import arteryfe_oracle as ao
+    from oracle.oracle_c import COracle
+    cfg = 'config/demo_arterybranch.cfg'
+    an = af.ArteryNetwork(af.ParamParser(cfg), wk_scale=(1, 1))
+    an.define_x()
+    assert (an._dev.na, an._dev.np, an.geo['Nt']) == (3, 401, 4000)
+    c = COracle(ao.network_from_cfg(cfg, wk_scale=(1, 1)))
+    _compare_with_c_oracle(an._dev, c, 4000, 500, counts_exact=False)
+    c.close()
+
+    cfg = 'config/demo_arterybranch_geo.cfg'
+    p = af.ParamParser(cfg)
+    p.param['R_term'] = 0.296
+    an = af.ArteryNetwork(p)
+    an.define_x()
+    assert (an._dev.na, an._dev.np, an.geo['Nt'], an.geo['N_cycles']) == (3, 201, 2000, 4)
+    c = COracle(ao.network_from_cfg(cfg, R_term=0.296))
+    _compare_with_c_oracle(an._dev, c, 8000, 1000, counts_exact=False)
+    c.close()
+
+
+def test_c5_members_over_both_cycles_match_c_oracle():
+    """BASELINE config 5 at its stated horizon: members of a batch of perturbed order-4 networks (Nx=100,
+    Nt=2000) over BOTH cardiac cycles (4 000 steps) against the C oracle run on the same perturbed
+    parameters -- state at the end, the stored outlet pressures of every leaf at all 200 dump steps, and
+    the artery Newton counts of every step."""
+    from bloodflow_b200 import ensemble as en
+    from bloodflow_b200.synthetic import tree_param
+    from oracle import arteryfe_oracle as ao
+    from oracle.oracle_c import COracle
+    base = tree_param(4, Nx=100, Nt=2000, N_cycles=2, Nt_store=100)
+    first, M, steps = 30000, 640, 4000
+    ens = en.EnsembleNetwork(base, M, first_index=first)
+    dev = ens.dev
+    ens.configure_store(2, 2)                       # both cycles: 200 snapshots
+    dev.set_counter_log(steps)
+    dev.step(0, steps)
+    A, q = dev.get_state()
+    art, jun, _ = dev.fetch_counter_log()
+    snaps = dev.fetch_snapshots()
+    op = snaps['outlet_pressure']                   # [snapshot, member, leaf]
+    leaves = np.asarray(ens.description['leaves'])
+    mask = ens.nominal.store_mask()
+    dump_steps = np.flatnonzero(np.tile(mask, 2))
+    assert op.shape[0] == len(dump_steps) == 200
+    np.testing.assert_array_equal(snaps['step'], dump_steps)
+    for m in (0, M // 3, M - 1):
+        p = en.perturb_param(base, first + m)
+        c = COracle(ao.OracleNetwork(p.param, p.geo, p.solution))
+        la, lj, po = [], [], []
+        done = 0
+        for s in dump_steps:
+            # the reference stores Un of time t_s, i.e. BEFORE the solve of step s (an:920-938)
+            if s > done:
+                failed, a_, j_ = c.step(done, s - done, nthreads=0, log=True)
+                assert not failed
+                la.append(a_)
+                lj.append(j_)
+                done = s
+            po.append(c.pressure()[leaves, -1])
+        failed, a_, j_ = c.step(done, steps - done, nthreads=0, log=True)
+        la.append(a_)
+        lj.append(j_)
+        Ao, qo = c.state()
+        np.testing.assert_allclose(A[m], Ao, rtol=1e-9, err_msg='member %d' % m)
+        np.testing.assert_allclose(q[m], qo, rtol=1e-9, atol=1e-9 * np.abs(qo).max(), err_msg='member %d' % m)
+        np.testing.assert_allclose(op[:, m], np.array(po), rtol=1e-9, err_msg='outlet pressure, member %d' % m)
+        np.testing.assert_array_equal(art[:, m], np.concatenate(la))
+        lj = np.concatenate(lj)
+        assert np.count_nonzero(jun[:, m] != lj) <= 1e-3 * lj.size and np.abs(jun[:, m] - lj).max() <= 1
+        c.close()
+    assert ens.flagged_members() == 0
