@@ -704,24 +704,53 @@ __device__ __forceinline__ double residual_pass(const ArteryCtx& c, const CellCo
                                                 const double* sA, const double* sq, double* ex, double* EA,
                                                 double* Eq) {
   const int tid = threadIdx.x, i0 = 4 * tid;
-  CellInt cell[4];
+  if constexpr (T == 32) {
+    // one-warp (ensemble) kernel: ONE copy of the cell routine and ONE of the row routine, each executed
+    // four times (16 independent one-warp CTAs per SM compete for the instruction cache, see cells_to_smem);
+    // the eight flux / source sums of the thread go through the exchange buffer: ex[(2k) T + t] = Gl,
+    // ex[(2k+1) T + t] = Gr of cell k
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const CellInt ci = artery_cell<T, false>(c, ccu, tab, S, sA, sq, i0 + k);
+      ex[(2 * k) * T + tid] = ci.Gl;
+      ex[(2 * k + 1) * T + tid] = ci.Gr;
+    }
+    cta_sync<T>();
+    double part = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k;
+      const int jm = vix<T>(i > 0 ? i - 1 : i), j0 = vix<T>(i), jp = vix<T>(i < 4 * T - 1 ? i + 1 : i);
+      CellInt lf, own;
+      lf.Gr = k > 0 ? ex[(2 * k - 1) * T + tid] : (tid > 0 ? ex[7 * T + tid - 1] : 0.0);
+      own.Gl = ex[(2 * k) * T + tid];
+      double ea = k == 0 ? EA[0] : (k == 1 ? EA[1] : (k == 2 ? EA[2] : EA[3]));
+      double eq = k == 0 ? Eq[0] : (k == 1 ? Eq[1] : (k == 2 ? Eq[2] : Eq[3]));
+      Row row;
+      build_row<false>(c, i, false, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], lf, own, ea, eq, row);
+      part += row.r[0] * row.r[0] + row.r[1] * row.r[1];
+    }
+    return part;
+  } else {
+    CellInt cell[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) cell[k] = artery_cell<T, false>(c, ccu, tab, S, sA, sq, i0 + k);
-  ex[tid] = cell[3].Gr;
-  cta_sync<T>();
-  CellInt left;
-  left.Gr = tid > 0 ? ex[tid - 1] : 0.0;
-  double part = 0.0;
+    for (int k = 0; k < 4; ++k) cell[k] = artery_cell<T, false>(c, ccu, tab, S, sA, sq, i0 + k);
+    ex[tid] = cell[3].Gr;
+    cta_sync<T>();
+    CellInt left;
+    left.Gr = tid > 0 ? ex[tid - 1] : 0.0;
+    double part = 0.0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = i0 + k;
-    const int jm = vix<T>(i > 0 ? i - 1 : i), j0 = vix<T>(i), jp = vix<T>(i < 4 * T - 1 ? i + 1 : i);
-    Row row;
-    const CellInt& lf = k == 0 ? left : cell[k > 0 ? k - 1 : 0];      // the cell to the left of vertex i
-    build_row<false>(c, i, false, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], lf, cell[k], EA[k], Eq[k], row);
-    part += row.r[0] * row.r[0] + row.r[1] * row.r[1];
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k;
+      const int jm = vix<T>(i > 0 ? i - 1 : i), j0 = vix<T>(i), jp = vix<T>(i < 4 * T - 1 ? i + 1 : i);
+      Row row;
+      const CellInt& lf = k == 0 ? left : cell[k > 0 ? k - 1 : 0];      // the cell to the left of vertex i
+      build_row<false>(c, i, false, sA[jm], sq[jm], sA[j0], sq[j0], sA[jp], sq[jp], lf, cell[k], EA[k], Eq[k], row);
+      part += row.r[0] * row.r[0] + row.r[1] * row.r[1];
+    }
+    return part;
   }
-  return part;
 }
 
 template <int T, bool FUSED>
