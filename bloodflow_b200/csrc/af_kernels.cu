@@ -50,6 +50,25 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// ---- Dirichlet mailbox (single networks with the dataflow flags).  The boundary -> artery hand-over
+// carries at most four doubles per artery, so the DATA is the flag: a junction / leaf task stores each
+// value with one relaxed 8-byte store the moment it is known (no fence, no separate flag, nothing else
+// written first), and lane k < 4 of the artery's first warp polls "its" slot until it no longer holds
+// the sentinel -- a NaN payload no arithmetic produces -- takes the value and puts the sentinel back.
+// Two slot sets alternate with the parity of the time step: the slot of step g is written again in
+// step g + 2, by a task that has acquired the f_art flag of the artery that reset it (release / acquire
+// chain through step g + 1), so the reset precedes that store in the coherence order of the location.
+// Measured on the order-8 tree (scripts/timeline.py): fence + three flag stores + the artery's acquire
+// and its re-load of nd.bc were 3.5 us of the 25 us junction <-> root-artery cycle that sets the step time.
+#define AF_MBOX_EMPTY 0xfff8deadbeef0001ull
+__device__ __forceinline__ void mbox_put(double* slot, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(slot), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long mbox_peek(const double* slot) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+  return v;
+}
 // Spin until *p >= want.  A failed run (fail_step set) ends every wait -- the producer may have left
 // early; so does an absurdly long wait (~1 s), which is reported as AF_FLAG_SYNC_TIMEOUT instead of
 // hanging the device.
@@ -64,6 +83,21 @@ __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned want, cons
   }
   fence_acq_rel_gpu();
 }
+
+#ifdef AF_TIMELINE
+__device__ __forceinline__ unsigned long long af_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define AF_TL(nd, gstep, task, slot)                                                                              \
+  do {                                                                                                           \
+    if ((nd).tl && (gstep) >= 0)                                                                                 \
+      (nd).tl[(((gstep) % (nd).tl_steps) * (size_t)((nd).na + (nd).nj + (nd).nl) + (task)) * 8 + (slot)] = af_globaltimer(); \
+  } while (0)
+#else
+#define AF_TL(nd, gstep, task, slot) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------
 // device view
@@ -106,7 +140,14 @@ struct NetDev {
   unsigned* f_art;
   unsigned* f_in;
   unsigned* f_out;
+  double* mbox;                   // [2][nb*na*4] Dirichlet mailbox, slot set = parity of the time step
   int dataflow;
+#ifdef AF_TIMELINE
+  // debug builds only (make timeline): %globaltimer stamps of the last tl_steps steps,
+  // tl[((g % tl_steps) * (na + nj + nl) + task) * 8 + slot]; tasks = arteries, junctions, leaves
+  unsigned long long* tl;
+  int tl_steps;
+#endif
   // solver constants
   double newton_rtol, newton_atol;
   int newton_max_it, junction_k_max, picard_k_max;
@@ -205,20 +246,26 @@ __global__ void k_setup_x(NetDev nd, const double* q0) {
 __device__ __forceinline__ void junction_finish(const NetDev& nd, int b, int j, const int* ia, const double* x,
                                                 double dex, int solves, uint32_t fl, int log_slot,
                                                 long long flag_step = -1) {
-  double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
-  for (int i = 0; i < 18; ++i) xg[i] = x[i];
   // set_inner_bc (an:762-764)
   int bp = b * nd.na + ia[0], b1 = b * nd.na + ia[1], b2 = b * nd.na + ia[2];
-  nd.bc[bp * 4 + 2] = x[9];  nd.bc[bp * 4 + 3] = x[0];
-  nd.bc[b1 * 4 + 0] = x[12]; nd.bc[b1 * 4 + 1] = x[3];
-  nd.bc[b2 * 4 + 0] = x[15]; nd.bc[b2 * 4 + 1] = x[6];
-  nd.dex[bp] = dex;    // the value a non-leaf vessel holds after set_bcs (SURVEY 9.4 item 8)
-  if (flag_step >= 0) {        // dataflow: the three artery ends may go on (one thread wrote everything above)
-    fence_acq_rel_gpu();
-    st_relaxed_u32(&nd.f_out[bp], (unsigned)(flag_step + 1));
-    st_relaxed_u32(&nd.f_in[b1], (unsigned)(flag_step + 1));
-    st_relaxed_u32(&nd.f_in[b2], (unsigned)(flag_step + 1));
+  if (flag_step >= 0) {
+    // dataflow: the six Dirichlet values go straight into the mailbox slots of the three artery ends,
+    // before anything else is written (the artery CTAs copy them into nd.bc)
+    double* mb = nd.mbox + (size_t)(flag_step & 1) * nd.nb * nd.na * 4;
+    mbox_put(&mb[bp * 4 + 2], x[9]);  mbox_put(&mb[bp * 4 + 3], x[0]);
+    mbox_put(&mb[b1 * 4 + 0], x[12]); mbox_put(&mb[b1 * 4 + 1], x[3]);
+    mbox_put(&mb[b2 * 4 + 0], x[15]); mbox_put(&mb[b2 * 4 + 1], x[6]);
+    AF_TL(nd, flag_step, nd.na + j, 4);
+  } else {
+    nd.bc[bp * 4 + 2] = x[9];  nd.bc[bp * 4 + 3] = x[0];
+    nd.bc[b1 * 4 + 0] = x[12]; nd.bc[b1 * 4 + 1] = x[3];
+    nd.bc[b2 * 4 + 0] = x[15]; nd.bc[b2 * 4 + 1] = x[6];
   }
+  double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
+  for (int i = 0; i < 18; ++i) xg[i] = x[i];
+  nd.dex[bp] = dex;    // the value a non-leaf vessel holds after set_bcs (SURVEY 9.4 item 8)
+  // the junction's own flag: its warm start x is complete for its next instance (which acquires it)
+  if (flag_step >= 0) st_release_u32(&nd.f_out[bp], (unsigned)(flag_step + 1));
   // bookkeeping nobody waits for: after the release, off the critical path of the step
   nd.j_solves[b * nd.nj + j] = solves;
   if (log_slot >= 0) nd.log_j[(size_t)log_slot * nd.nb * nd.nj + b * nd.nj + j] = solves;
@@ -279,7 +326,7 @@ __device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, 
 // so the boundary kernel fetches them before its grid-dependency wait.
 __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, int b, int j, const int* ia,
                                                     const Vessel& ves, const double* xg, double* x, double& dex,
-                                                    int& solves, uint32_t& fl) {
+                                                    int& solves, uint32_t& fl, long long tl_g = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v = lane % 3;
@@ -303,6 +350,7 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   solves = 0;
   int k = 0;
   bool singular = false;
+  if (lane == 0) AF_TL(nd, tl_g, nd.na + j, 2);
   for (; k < nd.junction_k_max; ++k) {
     // this lane's six unknowns, picked by selects: indexing x[] with the run-time v would
     // put the 18 unknowns into local memory for the whole Newton loop
@@ -333,6 +381,7 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
     ++solves;
   }
   if (k == nd.junction_k_max) fl |= AF_FLAG_JUNCTION_KMAX;
+  if (lane == 0) AF_TL(nd, tl_g, nd.na + j, 3);
   if (singular) {               // warp-uniform; the verbatim dense path owns the reference's singular branch
     for (int i = 0; i < 18; ++i) x[i] = xg[i];
     fl = 0;
@@ -346,7 +395,7 @@ __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, in
   int solves;
   uint32_t fl;
   const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
-  junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl);
+  junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl, flag_step);
   if ((threadIdx.x & 31) != 0) return;
   junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot, flag_step);
 }
@@ -408,11 +457,16 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   WkResult r;
   r.A_out = 0.0; r.dex = dex; r.its = 0; r.cycle = 0;
   if (lane != 0) return r;
+  AF_TL(nd, flag_step, nd.na + nd.nj + l, 2);
   const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
   r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
-  nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
+  AF_TL(nd, flag_step, nd.na + nd.nj + l, 3);
+  if (flag_step >= 0)      // dataflow: A_out (an:786) into the mailbox slot of the outlet (see junction_finish)
+    mbox_put(&nd.mbox[(size_t)(flag_step & 1) * nd.nb * nd.na * 4 + ba * 4 + 2], r.A_out);
+  else
+    nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
   nd.dex[ba] = r.dex;
-  if (flag_step >= 0) st_release_u32(&nd.f_out[ba], (unsigned)(flag_step + 1));
+  AF_TL(nd, flag_step, nd.na + nd.nj + l, 4);
   nd.picard_its[b * nd.nl + l] = r.its;
   if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
   atomicAdd(&nd.totals[2], (unsigned long long)r.its);
@@ -454,6 +508,10 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl, lo
     }
     const Vessel ves = nd.ves[ba];
     const bool dataflow = nd.dataflow && gstep >= 0;
+#ifdef AF_TIMELINE
+    const int tl_task = is_junction ? nd.na + j : nd.na + nd.nj + l;
+    if ((is_junction || is_leaf) && (threadIdx.x & 31) == 0) AF_TL(nd, gstep, tl_task, 0);
+#endif
     if (dataflow) {
       // Dataflow: no grid-wide wait.  The artery kernel of this step may become resident right away
       // (its CTAs wait for their own flags); this task waits for the arteries whose Un it reads --
@@ -461,7 +519,13 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl, lo
       cudaTriggerProgrammaticLaunchCompletion();
       if (is_junction || is_leaf) {
         if ((threadIdx.x & 31) < (is_junction ? 3 : 1)) wait_flag(&nd.f_art[ba], (unsigned)gstep, nd.fail_step, &nd.flags[b]);
+        // ... and, a junction, for the warm start x its own previous instance left (f_out of its parent vessel)
+        if (is_junction && (threadIdx.x & 31) == 3)
+          wait_flag(&nd.f_out[b * nd.na + ia[0]], (unsigned)gstep, nd.fail_step, &nd.flags[b]);
         __syncwarp();
+#ifdef AF_TIMELINE
+        if ((threadIdx.x & 31) == 0) AF_TL(nd, gstep, tl_task, 1);
+#endif
       }
     } else {
       cudaGridDependencySynchronize();
@@ -472,15 +536,9 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl, lo
     const long long flag_step = dataflow ? gstep : -1;
     if (nd.stop_on_fail && *(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) {
       // an artery solve failed: the run is over -- but nobody may be left waiting for this task
-      if (dataflow && (threadIdx.x & 31) == 0) {
-        if (is_junction) {
-          st_release_u32(&nd.f_out[b * nd.na + ia[0]], (unsigned)(gstep + 1));
-          st_release_u32(&nd.f_in[b * nd.na + ia[1]], (unsigned)(gstep + 1));
-          st_release_u32(&nd.f_in[b * nd.na + ia[2]], (unsigned)(gstep + 1));
-        } else if (is_leaf) {
-          st_release_u32(&nd.f_out[ba], (unsigned)(gstep + 1));
-        }
-      }
+      // (the artery CTAs polling their mailbox slots watch fail_step themselves)
+      if (dataflow && (threadIdx.x & 31) == 0 && is_junction)
+        st_release_u32(&nd.f_out[b * nd.na + ia[0]], (unsigned)(gstep + 1));
       return;
     }
     if (is_junction)
@@ -779,6 +837,10 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   const int ba = blockIdx.x + ba0;
   const int b = ba / nd.na, a = ba % nd.na;
   const bool dataflow = T > 32 && !FUSED && nd.dataflow && gstep >= 0;
+#ifdef AF_TIMELINE
+  const long long tl_g = (T > 32 && !FUSED && nd.nb == 1) ? gstep : -1;
+  if (tid == 0) AF_TL(nd, tl_g, a, 0);
+#endif
   if (T > 32 && nd.stop_on_fail && *(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) {
     if (dataflow && tid == 0) st_release_u32(&nd.f_art[ba], (unsigned)(gstep + 1));   // nobody may be left waiting
     return;
@@ -789,6 +851,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     if (tid == 0) wait_flag(&nd.f_art[ba], (unsigned)gstep, nd.fail_step, &nd.flags[b]);
     __syncthreads();
   }
+#ifdef AF_TIMELINE
+  if (tid == 0) AF_TL(nd, tl_g, a, 1);
+#endif
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
   {
@@ -908,19 +973,47 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       // first pass) only needs the previous artery kernel's output and has been
       // running under the boundary kernel of this step (programmatic dependent
       // launch); the Dirichlet data it writes is needed from here on.
+#ifdef AF_TIMELINE
+      if (tid == 0) AF_TL(nd, tl_g, a, 2);
+#endif
       if (dataflow) {
-        // the Dirichlet data of exactly this artery's two ends (the barrier below publishes the acquire)
-        if (tid == 0) {
-          if (!c.root) wait_flag(&nd.f_in[ba], (unsigned)(gstep + 1), nd.fail_step, &nd.flags[b]);
-          wait_flag(&nd.f_out[ba], (unsigned)(gstep + 1), nd.fail_step, &nd.flags[b]);
+        // the Dirichlet data of exactly this artery's two ends, from the mailbox: lane k < 4 polls slot k
+        // (A_in, q_in, A_out, q_out; ar:171-189 says which of them this artery has), takes the value, puts
+        // the sentinel back and keeps the holder array nd.bc up to date
+        if (tid < 4) {
+          double val;
+          if (tid < 2 ? !c.root : (tid == 2 || !c.leaf)) {
+            double* mb_slot = nd.mbox + (size_t)(gstep & 1) * nd.nb * nd.na * 4 + ba * 4 + tid;
+            unsigned long long u = mbox_peek(mb_slot);
+            for (unsigned spins = 0; u == AF_MBOX_EMPTY; ++spins) {
+              if ((spins & 63u) == 63u) {
+                if (*(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) break;
+                if (spins > (1u << 23)) { atomicOr(&nd.flags[b], AF_FLAG_SYNC_TIMEOUT); break; }
+              }
+              u = mbox_peek(mb_slot);
+            }
+            val = __longlong_as_double((long long)u);
+            mbox_put(mb_slot, __longlong_as_double((long long)AF_MBOX_EMPTY));
+            nd.bc[ba * 4 + tid] = val;
+          } else {
+            val = nd.bc[ba * 4 + tid];
+          }
+          bcv[tid] = val;
         }
         __syncthreads();
       } else {
         cudaGridDependencySynchronize();
       }
+#ifdef AF_TIMELINE
+      if (tid == 0) AF_TL(nd, tl_g, a, 3);
+#endif
       // Dirichlet values (ar:171-189); the root reads the inlet table (an:777, 916)
-      c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
-      c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
+      if (dataflow) {
+        c.gAin = bcv[0]; c.gqin = bcv[1]; c.gAout = bcv[2]; c.gqout = bcv[3];
+      } else {
+        c.gAin = nd.bc[ba * 4 + 0]; c.gqin = nd.bc[ba * 4 + 1];
+        c.gAout = nd.bc[ba * 4 + 2]; c.gqout = nd.bc[ba * 4 + 3];
+      }
       if (c.root && inlet_index >= 0) {
         c.gqin = nd.q_ins[(nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index];
         if (tid == 0) nd.bc[ba * 4 + 1] = c.gqin;      // arteries[0].q_in = q_in (an:777): the holder keeps it
@@ -929,6 +1022,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     cta_sync<T>();
     double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
     const double r2 = block_sum<T>(part, red);    // its two barriers also publish pa/pc
+#ifdef AF_TIMELINE
+    if (tid == 0 && first) AF_TL(nd, tl_g, a, 4);
+#endif
     if (test_here) {
       // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ----------
       const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
@@ -992,6 +1088,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     }
     cta_sync<T>();
     ++it;
+#ifdef AF_TIMELINE
+    if (tid == 0) AF_TL(nd, tl_g, a, 5);
+#endif
     // ---- convergence test after the update ([3P] NewtonSolver::converged), residual only ----------
     test_here = it < expect;          // too early to expect convergence: the next full pass tests
     if (!test_here) {
@@ -1003,6 +1102,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
     }
   }
+#ifdef AF_TIMELINE
+  if (tid == 0) AF_TL(nd, tl_g, a, 6);
+#endif
   // update_solution (ar:247-251): Un <- U, into the other buffer
   {
     double* gA = nd.A[cur ^ 1] + off;
@@ -1024,6 +1126,9 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
     nd.art_its[ba] = it;
     // the release is cumulative over what the other threads wrote before the barrier above
     if (dataflow) st_release_u32(&nd.f_art[ba], (unsigned)(gstep + 1));
+#ifdef AF_TIMELINE
+    AF_TL(nd, tl_g, a, 7);
+#endif
     // bookkeeping nobody waits for: after the release, off the critical path of the step
     if (log_slot >= 0) nd.log_art[(size_t)log_slot * nd.nb * nd.na + ba] = it;
     atomicAdd(&nd.totals[0], (unsigned long long)it);
@@ -1032,6 +1137,11 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       if (fl & AF_FLAG_ARTERY_NOCONV) atomicMin(nd.fail_step, (unsigned long long)(gstep >= 0 ? gstep : 0));
     }
   }
+}
+
+__global__ void k_fill_u64(unsigned long long* p, int n, unsigned long long v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 __global__ void k_set_flags(unsigned* p, int n, unsigned v) {
@@ -1758,6 +1868,7 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   AF_TRY(n->dalloc(&nd.f_art, nba));
   AF_TRY(n->dalloc(&nd.f_in, nba));
   AF_TRY(n->dalloc(&nd.f_out, nba));
+  AF_TRY(n->dalloc(&nd.mbox, nd.nb == 1 ? 2 * nba * 4 : 1));
   AF_TRY(n->dalloc(&n->scratch, 4096));
   {
     cudaError_t ea = n->arena_flush();         // before the memsets below: the mirror holds zeros there
@@ -1801,9 +1912,10 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   // multi-warp artery kernel (AF_NO_DATAFLOW=1: the plain programmatic-dependent-launch chain)
   nd.dataflow = (nd.nb == 1 && n->boundary_lanes == 32 && n->artery_threads >= 64 && !n->fused) ? 1 : 0;
   if (const char* env = getenv("AF_NO_DATAFLOW")) if (atoi(env)) nd.dataflow = 0;
-  // measured on the order-8 tree with the flags (whole cycle / systolic window): 64 threads 23.84 / 27.3 us per
-  // step, 128: 26.96 (window), 256: 23.60 / 26.35; without the flags the CTA size has no effect (25.5 us)
-  if (nd.dataflow) n->boundary_block = 256;
+  // measured on the order-8 tree, whole cycle: with the flags alone 64 threads 23.84 us per step, 256: 23.60;
+  // with the Dirichlet mailbox 64: 23.21, 128: 23.08, 256: 23.35 (same box); without the flags the CTA size
+  // has no effect (25.5 us)
+  if (nd.dataflow) n->boundary_block = 128;
   // sub-streams for ensembles: every share must still fill the machine (148 SMs x 16 one-warp CTAs) twice over
   if (n->boundary_lanes == 1) {
     const long long ctas = (long long)nd.nb * nd.na, fill = 2LL * 148 * AF_T32_BLOCKS;
@@ -1822,6 +1934,16 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
     }
     if (es != cudaSuccess) { af_net_destroy(n); return fail(AF_ECUDA, std::string("sub-streams: ") + cudaGetErrorString(es)); }
   }
+#ifdef AF_TIMELINE
+  nd.tl = nullptr; nd.tl_steps = 0;
+  if (const char* env = getenv("AF_TIMELINE_STEPS")) {
+    int v = atoi(env);
+    if (v > 0 && nd.nb == 1) {
+      nd.tl_steps = v;
+      AF_TRY(n->dalloc(&nd.tl, (size_t)v * (nd.na + nd.nj + nd.nl) * 8));
+    }
+  }
+#endif
   if (const char* env = getenv("AF_BOUNDARY_BLOCK")) {
     int v = atoi(env);
     if (v >= 32 && v <= 256 && v % 32 == 0) n->boundary_block = v;
@@ -1875,6 +1997,18 @@ static int check(af_net* n) {
   AF_CUDA(cudaSetDevice(n->device));
   return AF_OK;
 }
+
+#ifdef AF_TIMELINE
+// debug builds only: the %globaltimer stamps, [tl_steps][na + nj + nl][8]
+extern "C" int af_net_debug_timeline(af_net* n, unsigned long long* out, int64_t count) {
+  int rc = check(n);
+  if (rc) return rc;
+  if (!n->nd.tl) return fail(AF_ESTATE, "no timeline (AF_TIMELINE_STEPS)");
+  AF_CUDA(cudaStreamSynchronize(n->stream));
+  AF_CUDA(cudaMemcpy(out, n->nd.tl, (size_t)count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return AF_OK;
+}
+#endif
 
 extern "C" int af_net_sync(af_net* n) {
   int rc = check(n);
@@ -2018,6 +2152,7 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_art, nba, (unsigned)n_first);
     k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_in, nba, (unsigned)n_first);
     k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_out, nba, (unsigned)n_first);
+    k_fill_u64<<<(8 * nba + 127) / 128, 128, 0, n->stream>>>((unsigned long long*)n->nd.mbox, 8 * nba, AF_MBOX_EMPTY);
     AF_CUDA(cudaGetLastError());
   }
   const bool split = n->n_sub > 1 && n_steps > 0;
