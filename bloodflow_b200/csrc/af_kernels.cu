@@ -69,17 +69,44 @@ __device__ __forceinline__ unsigned long long mbox_peek(const double* slot) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
   return v;
 }
+#ifndef AF_POLL_SLEEP_NS
+#define AF_POLL_SLEEP_NS 100
+#endif
+#ifndef AF_POLL_SLEEP_NS_JUNCTION
+#define AF_POLL_SLEEP_NS_JUNCTION 0
+#endif
 // Spin until *p >= want.  A failed run (fail_step set) ends every wait -- the producer may have left
 // early; so does an absurdly long wait (~1 s), which is reported as AF_FLAG_SYNC_TIMEOUT instead of
 // hanging the device.
 #define AF_FLAG_SYNC_TIMEOUT 64u
+template <bool SLEEP = false>
 __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned want, const unsigned long long* fail_step,
                                           uint32_t* status) {
   for (unsigned spins = 0; (int)(ld_relaxed_u32(p) - want) < 0; ++spins) {
     if ((spins & 63u) == 63u) {
       if (*(volatile const unsigned long long*)fail_step != AF_NO_FAIL) return;
-      if (spins > (1u << 23)) { atomicOr(status, AF_FLAG_SYNC_TIMEOUT); return; }
+      if (spins > (1u << (SLEEP ? 22 : 23))) { atomicOr(status, AF_FLAG_SYNC_TIMEOUT); return; }
     }
+    if (SLEEP) __nanosleep(AF_POLL_SLEEP_NS);     // persistent kernels: a waiting warp must not disturb its neighbours
+  }
+  fence_acq_rel_gpu();
+}
+
+// The same wait for a whole warp, every lane on its own flag, with a warp-UNIFORM exit (vote): the lanes of a
+// junction warp leave the loop together, so the warp is converged for the shuffles that follow.
+__device__ __forceinline__ void wait_flag_warp(const unsigned* p, unsigned want, const unsigned long long* fail_step,
+                                               uint32_t* status) {
+  for (unsigned spins = 0;; ++spins) {
+    const bool ok = (int)(ld_relaxed_u32(p) - want) >= 0;
+    if (__all_sync(0xffffffffu, ok)) break;
+    if ((spins & 63u) == 63u) {
+      if (*(volatile const unsigned long long*)fail_step != AF_NO_FAIL) break;       // same address in every lane: uniform
+      if (spins > (1u << 22)) {
+        if ((threadIdx.x & 31) == 0) atomicOr(status, AF_FLAG_SYNC_TIMEOUT);
+        break;
+      }
+    }
+    if (AF_POLL_SLEEP_NS_JUNCTION) __nanosleep(AF_POLL_SLEEP_NS_JUNCTION);
   }
   fence_acq_rel_gpu();
 }
@@ -352,6 +379,9 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   bool singular = false;
   if (lane == 0) AF_TL(nd, tl_g, nd.na + j, 2);
   for (; k < nd.junction_k_max; ++k) {
+#ifdef AF_TIMELINE
+    if (lane == 0 && (k == 1 || k == 2)) AF_TL(nd, tl_g, nd.na + j, 4 + k);
+#endif
     // this lane's six unknowns, picked by selects: indexing x[] with the run-time v would
     // put the 18 unknowns into local memory for the whole Newton loop
 #define AF_PICK3(a, b, c) (v == 0 ? (a) : (v == 1 ? (b) : (c)))
@@ -382,10 +412,19 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   }
   if (k == nd.junction_k_max) fl |= AF_FLAG_JUNCTION_KMAX;
   if (lane == 0) AF_TL(nd, tl_g, nd.na + j, 3);
+#ifdef AF_TIMELINE
+  if (lane == 0 && nd.tl && tl_g >= 0)
+    nd.tl[((tl_g % nd.tl_steps) * (size_t)(nd.na + nd.nj + nd.nl) + nd.na + j) * 8 + 7] = (unsigned long long)k;
+#endif
   if (singular) {               // warp-uniform; the verbatim dense path owns the reference's singular branch
-    for (int i = 0; i < 18; ++i) x[i] = xg[i];
-    fl = 0;
-    solves = junction_slow_path(nd, cur, b, ia, dex, x, &fl);
+    // (through copies: handing x itself to the out-of-line routine would make it addressable and put the
+    // 18 unknowns into local memory for the whole Newton loop above)
+    double xs[18];
+    uint32_t fls = 0;
+    for (int i = 0; i < 18; ++i) xs[i] = xg[i];
+    solves = junction_slow_path(nd, cur, b, ia, dex, xs, &fls);
+    for (int i = 0; i < 18; ++i) x[i] = xs[i];
+    fl = fls;
   }
 }
 
@@ -396,8 +435,11 @@ __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, in
   uint32_t fl;
   const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
   junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl, flag_step);
-  if ((threadIdx.x & 31) != 0) return;
-  junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot, flag_step);
+  // (an if-block, not an early return: inside the step loop of k_junction_p the warp must be converged
+  // again afterwards -- with lane 0 on a path of its own every __shfl_sync of the next step took its
+  // divergent slow path and a Newton iteration cost 7.5 us instead of 0.9 us)
+  if ((threadIdx.x & 31) == 0) junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot, flag_step);
+  __syncwarp();
 }
 
 __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int l, int log_slot) {
@@ -811,6 +853,120 @@ __device__ __forceinline__ double residual_pass(const ArteryCtx& c, const CellCo
   }
 }
 
+// The Newton iteration of one artery on the iterate U in shared memory ([3P] NewtonSolver on the form of
+// ar:191-230; one CTA, four vertices per thread).  `dirichlet_hook` runs once, after the cell integrals of
+// the first pass (which need no Dirichlet data): it waits for / fetches the Dirichlet values into `c` and
+// must leave the CTA converged (the barrier that follows it publishes the cells).  `expect` = linear solves
+// this artery needed in the previous time step.  Returns the number of linear solves; `fl` gets AF_FLAG_* bits.
+template <int T, class Hook>
+__device__ __forceinline__ int artery_newton(const NetDev& nd, ArteryCtx& c, const CellCoef& ccu, const double* tab,
+                                             int S, double* sA, double* sq, double* Lo, double* pa, double* pb,
+                                             double* pc, double* red, int expect, uint32_t& fl, Hook&& dirichlet_hook,
+                                             long long tl_g, int a) {
+  const int tid = threadIdx.x;
+  double EA[4], Eq[4];          // explicit part of the residual of the own vertices
+  int it = 0;
+  double r_first = 0.0;
+  fl = 0;
+  // How many linear solves this artery needed in the previous time step: the convergence test after
+  // solve number `expect` (and later ones) is done by the lean residual-only pass at the bottom of the
+  // loop -- it will most likely say "converged", and a full pass there would assemble a Jacobian and
+  // eliminate half the rows for nothing.  Before that the test is part of the full pass that the next
+  // solve needs anyway.  The prediction only selects which code computes ||R||; the iterates, the tests
+  // and the count are those of [3P] NewtonSolver either way.
+  bool test_here = true;
+  for (;;) {
+    const bool first = (it == 0);
+    // ---- full pass: cells -> shared memory, then rows (residual + Jacobian) and level 0 of the reduction
+    Row rb, rd;
+    cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
+    if (first) dirichlet_hook();
+    cta_sync<T>();
+    double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
+    const double r2 = block_sum<T>(part, red);    // its two barriers also publish pa/pc
+#ifdef AF_TIMELINE
+    if (tid == 0 && first) AF_TL(nd, tl_g, a, 4);
+#endif
+    if (test_here) {
+      // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ----------
+      const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
+      if (first) r_first = r;
+      if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
+      if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
+      if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
+    }
+    // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------
+    if (tid + 1 < T) {
+      Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
+      apply_right(rd, en);
+    }
+    {
+      Elim eb = make_elim(rb);
+      park(pb, T, tid, eb);
+      apply_left(rd, eb);
+    }
+    cta_sync<T>();
+    if (tid + 1 < T) {
+      Elim en = unpark(pb, T, tid + 1);      // vertex b of the next thread
+      apply_right(rd, en);
+    }
+    // ---- the reduced system (one row per thread): parallel cyclic reduction ---
+    // The row stays in registers.  In step s = 1, 2, 4, ... every thread turns
+    // its row into x_t = g - P x_{t-s} - Q x_{t+s}, publishes (P, Q, g) and
+    // eliminates both neighbours at distance s; after log2(T) steps the rows are
+    // decoupled.  All warps stay busy and there is no backward sweep: on this
+    // latency-bound kernel the shorter serial chain beats the work-optimal
+    // cyclic reduction (profiles/README.md).
+    double xd[2], xl[2] = {0.0, 0.0};
+    {
+      double* buf = Lo;                       // 10T doubles of the 14T scratch
+#pragma unroll 1
+      for (int sdist = 1; sdist < T; sdist *= 2) {
+        park(buf, T, tid, make_elim(rd));
+        cta_sync<T>();
+        const bool more = 2 * sdist < T;       // the last step leaves rows that are never coupled again
+        if (tid >= sdist) apply_left(rd, unpark(buf, T, tid - sdist), more);
+        if (tid + sdist < T) apply_right(rd, unpark(buf, T, tid + sdist), more);
+        cta_sync<T>();
+      }
+      double inv[4];
+      inv2v(rd.dg, inv);
+      xd[0] = inv[0] * rd.r[0] + inv[1] * rd.r[1];
+      xd[1] = inv[2] * rd.r[0] + inv[3] * rd.r[1];
+      buf[tid] = xd[0]; buf[T + tid] = xd[1];
+      cta_sync<T>();
+      if (tid > 0) { xl[0] = buf[tid - 1]; xl[1] = buf[T + tid - 1]; }
+    }
+    // ---- back-substitution of the own vertices, U -= dU ----------------------
+    {
+      double xa[2], xb[2], xc[2];
+      back_sub(unpark(pb, T, tid), xl, xd, xb);
+      back_sub(unpark(pa, T, tid), xl, xb, xa);
+      back_sub(unpark(pc, T, tid), xb, xd, xc);
+      sA[tid] -= xa[0]; sq[tid] -= xa[1];
+      sA[T + tid] -= xb[0]; sq[T + tid] -= xb[1];
+      sA[2 * T + tid] -= xc[0]; sq[2 * T + tid] -= xc[1];
+      sA[3 * T + tid] -= xd[0]; sq[3 * T + tid] -= xd[1];
+    }
+    cta_sync<T>();
+    ++it;
+#ifdef AF_TIMELINE
+    if (tid == 0) AF_TL(nd, tl_g, a, 5);
+#endif
+    // ---- convergence test after the update ([3P] NewtonSolver::converged), residual only ----------
+    test_here = it < expect;          // too early to expect convergence: the next full pass tests
+    if (!test_here) {
+      const double part2 = residual_pass<T>(c, ccu, tab, S, sA, sq, Lo, EA, Eq);
+      const double q2 = block_sum<T>(part2, red);
+      const double r = q2 > 0.0 ? af_sqrt_pos(q2) : q2;
+      if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
+      if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
+      if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
+    }
+  }
+  return it;
+}
+
 template <int T, bool FUSED>
 __global__ void __launch_bounds__(T, (T == 32 ? AF_T32_BLOCKS : (T <= 256 ? 512 / T : 1)))
 k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long gstep) {
@@ -948,27 +1104,16 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
   for (int g = 0; g < 3; ++g) { ccu.c1[g] = c.c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
   const int slot = nd.coef_slot[ba];
   const double* tab = slot >= 0 ? nd.cellcoef + (size_t)slot * 9 * S : nullptr;
-  double EA[4], Eq[4];          // explicit part of the residual of the own vertices
   cta_sync<T>();
 
-  int it = 0;
-  double r_first = 0.0;
-  uint32_t fl = 0;
-  // How many linear solves this artery needed in the previous time step: the convergence test after
-  // solve number `expect` (and later ones) is done by the lean residual-only pass at the bottom of the
-  // loop -- it will most likely say "converged", and a full pass there would assemble a Jacobian and
-  // eliminate half the rows for nothing.  Before that the test is part of the full pass that the next
-  // solve needs anyway.  The prediction only selects which code computes ||R||; the iterates, the tests
-  // and the count are those of [3P] NewtonSolver either way.
+  // How many linear solves this artery needed in the previous time step (see artery_newton)
   const int prev_its = nd.art_its[ba];
-  const int expect = prev_its > 1 ? prev_its : 1;
-  bool test_here = true;
-  for (;;) {
-    const bool first = (it == 0);
-    // ---- full pass: cells -> shared memory, then rows (residual + Jacobian) and level 0 of the reduction
-    Row rb, rd;
-    cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
-    if (!FUSED && first) {
+  uint32_t fl = 0;
+#ifndef AF_TIMELINE
+  const long long tl_g = -1;
+#endif
+  const int it = artery_newton<T>(nd, c, ccu, tab, S, sA, sq, Lo, pa, pb, pc, red, prev_its > 1 ? prev_its : 1, fl, [&]() {
+    if (!FUSED) {
       // Everything up to here (vessel constants, U <- Un, the cell integrals of the
       // first pass) only needs the previous artery kernel's output and has been
       // running under the boundary kernel of this step (programmatic dependent
@@ -1019,89 +1164,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
         if (tid == 0) nd.bc[ba * 4 + 1] = c.gqin;      // arteries[0].q_in = q_in (an:777): the holder keeps it
       }
     }
-    cta_sync<T>();
-    double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
-    const double r2 = block_sum<T>(part, red);    // its two barriers also publish pa/pc
-#ifdef AF_TIMELINE
-    if (tid == 0 && first) AF_TL(nd, tl_g, a, 4);
-#endif
-    if (test_here) {
-      // ---- [3P] NewtonSolver::converged: r/r0 < rtol or r < atol ----------
-      const double r = r2 > 0.0 ? af_sqrt_pos(r2) : r2;     // branch-free sqrt; 0 and NaN pass through
-      if (first) r_first = r;
-      if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
-      if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
-      if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
-    }
-    // ---- cyclic reduction, rest of level 0 and level 1 in registers -----------
-    if (tid + 1 < T) {
-      Elim en = unpark(pa, T, tid + 1);      // vertex a of the next thread
-      apply_right(rd, en);
-    }
-    {
-      Elim eb = make_elim(rb);
-      park(pb, T, tid, eb);
-      apply_left(rd, eb);
-    }
-    cta_sync<T>();
-    if (tid + 1 < T) {
-      Elim en = unpark(pb, T, tid + 1);      // vertex b of the next thread
-      apply_right(rd, en);
-    }
-    // ---- the reduced system (one row per thread): parallel cyclic reduction ---
-    // The row stays in registers.  In step s = 1, 2, 4, ... every thread turns
-    // its row into x_t = g - P x_{t-s} - Q x_{t+s}, publishes (P, Q, g) and
-    // eliminates both neighbours at distance s; after log2(T) steps the rows are
-    // decoupled.  All warps stay busy and there is no backward sweep: on this
-    // latency-bound kernel the shorter serial chain beats the work-optimal
-    // cyclic reduction (profiles/README.md).
-    double xd[2], xl[2] = {0.0, 0.0};
-    {
-      double* buf = Lo;                       // 10T doubles of the 14T scratch
-#pragma unroll 1
-      for (int sdist = 1; sdist < T; sdist *= 2) {
-        park(buf, T, tid, make_elim(rd));
-        cta_sync<T>();
-        const bool more = 2 * sdist < T;       // the last step leaves rows that are never coupled again
-        if (tid >= sdist) apply_left(rd, unpark(buf, T, tid - sdist), more);
-        if (tid + sdist < T) apply_right(rd, unpark(buf, T, tid + sdist), more);
-        cta_sync<T>();
-      }
-      double inv[4];
-      inv2v(rd.dg, inv);
-      xd[0] = inv[0] * rd.r[0] + inv[1] * rd.r[1];
-      xd[1] = inv[2] * rd.r[0] + inv[3] * rd.r[1];
-      buf[tid] = xd[0]; buf[T + tid] = xd[1];
-      cta_sync<T>();
-      if (tid > 0) { xl[0] = buf[tid - 1]; xl[1] = buf[T + tid - 1]; }
-    }
-    // ---- back-substitution of the own vertices, U -= dU ----------------------
-    {
-      double xa[2], xb[2], xc[2];
-      back_sub(unpark(pb, T, tid), xl, xd, xb);
-      back_sub(unpark(pa, T, tid), xl, xb, xa);
-      back_sub(unpark(pc, T, tid), xb, xd, xc);
-      sA[tid] -= xa[0]; sq[tid] -= xa[1];
-      sA[T + tid] -= xb[0]; sq[T + tid] -= xb[1];
-      sA[2 * T + tid] -= xc[0]; sq[2 * T + tid] -= xc[1];
-      sA[3 * T + tid] -= xd[0]; sq[3 * T + tid] -= xd[1];
-    }
-    cta_sync<T>();
-    ++it;
-#ifdef AF_TIMELINE
-    if (tid == 0) AF_TL(nd, tl_g, a, 5);
-#endif
-    // ---- convergence test after the update ([3P] NewtonSolver::converged), residual only ----------
-    test_here = it < expect;          // too early to expect convergence: the next full pass tests
-    if (!test_here) {
-      const double part2 = residual_pass<T>(c, ccu, tab, S, sA, sq, Lo, EA, Eq);
-      const double q2 = block_sum<T>(part2, red);
-      const double r = q2 > 0.0 ? af_sqrt_pos(q2) : q2;
-      if (r < nd.newton_rtol * r_first || r < nd.newton_atol) break;
-      if (!(r == r) || r > 1.0e300) { fl = AF_FLAG_NONFINITE | AF_FLAG_ARTERY_NOCONV; break; }
-      if (it >= nd.newton_max_it) { fl = AF_FLAG_ARTERY_NOCONV; break; }
-    }
-  }
+  }, tl_g, a);
 #ifdef AF_TIMELINE
   if (tid == 0) AF_TL(nd, tl_g, a, 6);
 #endif
@@ -1136,6 +1199,190 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       atomicOr(&nd.flags[b], fl);
       if (fl & AF_FLAG_ARTERY_NOCONV) atomicMin(nd.fail_step, (unsigned long long)(gstep >= 0 ? gstep : 0));
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent time loop of a single network: ONE launch of k_artery_p (a CTA per artery) and one of
+// k_junction_p (a warp per junction) advance a whole chunk of time steps.  Everything that ordered the
+// per-step launches is already in global memory -- f_art[artery] counts the steps an artery has completed,
+// the Dirichlet mailbox carries junction results -- so the kernels simply loop.  What it buys
+// (scripts/timeline.py on the per-step launches): the CTA of step n+1 of an artery could only start once
+// the boundary kernel of step n+1 was completely resident, which in turn needed SMs drained of step-n artery
+// CTAs -- the root artery re-started 6.4 us after it had released its previous step, and that re-start, not the
+// junction solve (done after 7.2 us), set the 22.4 us period of the root <-> first-junction cycle.  Here
+// the iterate stays in shared memory between steps (Un is still written out: the junctions and the dumps read
+// it), vessel constants stay in registers, and a leaf artery runs its own Windkessel (its second warp, while
+// the others integrate cells) -- with the leaf tasks in a kernel of their own the two kernels would not fit
+// the register files together (255 x 32 K + 255 warps x 8 K > 148 x 64 K).  All CTAs of both kernels must be
+// co-resident (af_net_create checks; otherwise the per-step launches are used): an artery spins on its
+// mailbox, a junction on its arteries' flags; a failed run or a ~1 s wait ends every spin.
+// ---------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T, (T <= 256 ? 512 / T : 1))
+k_artery_p(NetDev nd, int cur, long long g0, int n_steps, int log_slot0, int n_log) {
+  extern __shared__ double sm[];
+  __shared__ double red[32];
+  __shared__ double bcv[4];
+  __shared__ double qin_s;
+  __shared__ int stop_s;
+  constexpr int NV = 4 * T;
+  const int np = nd.np, ne = nd.Nx, S = nd.S;
+  const int tid = threadIdx.x;
+  double* sA = sm;
+  double* sq = sA + NV;
+  double* Lo = sq + NV;
+  double* pa = Lo + 10 * T;
+  double* pb = pa + 10 * T;
+  double* pc = pb + 10 * T;
+  // the junction kernel of this chunk follows in the stream as a programmatic dependent launch
+  cudaTriggerProgrammaticLaunchCompletion();
+  const int ba = blockIdx.x, b = 0, a = ba;
+  const Vessel v = nd.ves[ba];
+  const size_t off = (size_t)ba * S;
+  {
+    // U <- Un (ar:158), once per chunk: afterwards the converged iterate of a step IS the next initial guess
+    const double* gA = nd.A[cur] + off;
+    const double* gq = nd.q[cur] + off;
+    const int i0 = 4 * tid;
+    double va[4] = {1.0, 1.0, 1.0, 1.0}, vq[4] = {0.0, 0.0, 0.0, 0.0};     // padding vertices
+    if (i0 + 3 < np) {
+      const double2 a01 = *reinterpret_cast<const double2*>(gA + i0), a23 = *reinterpret_cast<const double2*>(gA + i0 + 2);
+      const double2 q01 = *reinterpret_cast<const double2*>(gq + i0), q23 = *reinterpret_cast<const double2*>(gq + i0 + 2);
+      va[0] = a01.x; va[1] = a01.y; va[2] = a23.x; va[3] = a23.y;
+      vq[0] = q01.x; vq[1] = q01.y; vq[2] = q23.x; vq[3] = q23.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k < np) { va[k] = gA[i0 + k]; vq[k] = gq[i0 + k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sA[k * T + tid] = va[k]; sq[k * T + tid] = vq[k]; }
+  }
+  ArteryCtx c;
+  c.ne = ne; c.np = np;
+  c.h = v.dx; c.Kr = -v.src_k;
+  c.dth = nd.dt * nd.theta; c.dte = nd.dt * (1.0 - nd.theta);
+  c.c1_0 = v.f0 * sqrt(v.A00); c.c1_L = v.fL * sqrt(v.A0L);
+  c.root = (a == nd.root_artery); c.leaf = nd.art_leaf[a] >= 0;
+  CellCoef ccu;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) { ccu.c1[g] = c.c1_0; ccu.t2[g] = 0.0; ccu.t3[g] = 0.0; }
+  const int slot = nd.coef_slot[ba];
+  const double* tab = slot >= 0 ? nd.cellcoef + (size_t)slot * 9 * S : nullptr;
+  int prev_its = nd.art_its[ba];
+  // holder values that no junction / leaf delivers keep what they were (root: A_in; leaf: q_out)
+  if (tid < 4) bcv[tid] = nd.bc[ba * 4 + tid];
+  const int n_wait = nd.nj > 0 || nd.nl > 0;     // (a lone vessel without outlet model has nothing to wait for)
+  (void)n_wait;
+  for (int s = 0; s < n_steps; ++s, cur ^= 1) {
+    const long long g = g0 + s;
+    // a failed artery solve ends the run at its step (DOLFIN raises there, ar:244)
+    if (tid == 0) stop_s = nd.stop_on_fail && *(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL;
+    __syncthreads();
+    if (stop_s) break;
+    const int log_slot = s < n_log ? log_slot0 + s : -1;
+    const int inlet_index = (int)((g % nd.Nt + 1) % nd.Nt);                 // an:916
+    if (tid == 0) { AF_TL(nd, g, a, 0); AF_TL(nd, g, a, 1); }
+    if (c.root && tid == 0) {
+      // the inlet sample of this step, fetched asynchronously into shared memory (consumed after the cells)
+      const double* src = nd.q_ins + (nd.q_ins_per_net ? (size_t)b * nd.Nt : 0) + inlet_index;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&qin_s);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    }
+    if (c.leaf && (tid >> 5) == 1) {
+      // set_bcs of a leaf (an:780-786): its Windkessel needs nothing but this artery's own Un, which this
+      // CTA wrote (and published with a barrier) at the end of the previous step
+      WkResult r = leaf_solve_warp(nd, cur, b, nd.art_leaf[a], ba, v, log_slot, -1);
+      if ((tid & 31) == 0) bcv[2] = r.A_out;
+    }
+    uint32_t fl = 0;
+    const int it = artery_newton<T>(nd, c, ccu, tab, S, sA, sq, Lo, pa, pb, pc, red, prev_its > 1 ? prev_its : 1, fl, [&]() {
+      if (tid == 0) AF_TL(nd, g, a, 2);
+      if (tid < 4 && (tid < 2 ? !c.root : !c.leaf)) {
+        // Dirichlet values from the mailbox (see k_artery)
+        double* mb_slot = nd.mbox + (size_t)(g & 1) * nd.nb * nd.na * 4 + ba * 4 + tid;
+        unsigned long long u = mbox_peek(mb_slot);
+        for (unsigned spins = 0; u == AF_MBOX_EMPTY; ++spins) {
+          if ((spins & 63u) == 63u) {
+            if (*(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) break;
+            if (spins > (1u << 22)) { atomicOr(&nd.flags[b], AF_FLAG_SYNC_TIMEOUT); break; }
+          }
+          // a waiting CTA must be quiet: with all 255 artery CTAs resident and polling back to back the junction
+          // warps next to them ran 10x slower (scripts/timeline.py: 22 us instead of 2.2 us per junction Newton)
+          __nanosleep(AF_POLL_SLEEP_NS);
+          u = mbox_peek(mb_slot);
+        }
+        const double val = __longlong_as_double((long long)u);
+        mbox_put(mb_slot, __longlong_as_double((long long)AF_MBOX_EMPTY));
+        nd.bc[ba * 4 + tid] = val;
+        bcv[tid] = val;
+      }
+      if (c.root && tid == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) AF_TL(nd, g, a, 3);
+      c.gAin = bcv[0]; c.gqin = bcv[1]; c.gAout = bcv[2]; c.gqout = bcv[3];
+      if (c.root) {
+        c.gqin = qin_s;
+        if (tid == 0) nd.bc[ba * 4 + 1] = c.gqin;      // arteries[0].q_in = q_in (an:777): the holder keeps it
+      }
+    }, g, a);
+    if (tid == 0) AF_TL(nd, g, a, 6);
+    // update_solution (ar:247-251): Un <- U, into the other buffer
+    {
+      double* gA = nd.A[cur ^ 1] + off;
+      double* gq = nd.q[cur ^ 1] + off;
+      const int i0 = 4 * tid;
+      if (i0 + 3 < np) {
+        *reinterpret_cast<double2*>(gA + i0) = make_double2(sA[tid], sA[T + tid]);
+        *reinterpret_cast<double2*>(gA + i0 + 2) = make_double2(sA[2 * T + tid], sA[3 * T + tid]);
+        *reinterpret_cast<double2*>(gq + i0) = make_double2(sq[tid], sq[T + tid]);
+        *reinterpret_cast<double2*>(gq + i0 + 2) = make_double2(sq[2 * T + tid], sq[3 * T + tid]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i0 + k < np) { gA[i0 + k] = sA[k * T + tid]; gq[i0 + k] = sq[k * T + tid]; }
+      }
+    }
+    __syncthreads();        // every thread's part of Un is written before thread 0 releases it
+    if (tid == 0) {
+      nd.art_its[ba] = it;
+      st_release_u32(&nd.f_art[ba], (unsigned)(g + 1));
+      AF_TL(nd, g, a, 7);
+      if (log_slot >= 0) nd.log_art[(size_t)log_slot * nd.nb * nd.na + ba] = it;
+      atomicAdd(&nd.totals[0], (unsigned long long)it);
+      if (fl) {
+        atomicOr(&nd.flags[b], fl);
+        if (fl & AF_FLAG_ARTERY_NOCONV) atomicMin(nd.fail_step, (unsigned long long)g);
+      }
+    }
+    prev_its = it;
+  }
+}
+
+// one warp per junction, looping over the steps of the chunk (see k_artery_p)
+__global__ void __launch_bounds__(128) k_junction_p(NetDev nd, int cur, long long g0, int n_steps, int log_slot0, int n_log) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (j >= nd.nj) return;
+  const int b = 0, v = lane % 3;
+  const int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
+  const int ba = v == 0 ? ia[0] : (v == 1 ? ia[1] : ia[2]);
+  for (int s = 0; s < n_steps; ++s, cur ^= 1) {
+    const long long g = g0 + s;
+    if (nd.stop_on_fail && *(volatile const unsigned long long*)nd.fail_step != AF_NO_FAIL) break;
+    if (lane == 0) AF_TL(nd, g, nd.na + j, 0);
+    // the vessel constants are fetched again every step, before the wait: kept in registers across the
+    // loop they cost 270 B of spills inside the Newton iteration
+    const Vessel ves = nd.ves[ba];
+    // the three vessels must have completed step g - 1 (lane v waits for vessel v); the barrier also orders
+    // this warp's own warm start x, written by lane 0 at the end of the previous step
+    // (every lane polls the flag of "its" vessel lane % 3: no divergent region around the wait)
+    wait_flag_warp(&nd.f_art[ba], (unsigned)g, nd.fail_step, &nd.flags[b]);
+    __syncwarp();
+    if (lane == 0) AF_TL(nd, g, nd.na + j, 1);
+    junction_task_warp(nd, cur, b, j, ia, ves, s < n_log ? log_slot0 + s : -1, g);
+    __syncwarp();
   }
 }
 
@@ -1493,6 +1740,8 @@ struct af_net {
   int boundary_lanes = 32;
   bool pdl = true;                 // programmatic dependent launch of k_artery (AF_NO_PDL=1 disables)
   bool fused = false;              // af_net_step: set_bcs inside the artery CTAs (single networks)
+  bool persist = false;            // af_net_step: persistent kernels over chunks of steps (k_artery_p / k_junction_p)
+  static const int kChunk = 64;    // steps per launch pair of the persistent path (failure polling granularity)
   int boundary_block = 64;         // threads per CTA of k_boundary (AF_BOUNDARY_BLOCK overrides)
   // Ensembles: the member range is cut into n_sub contiguous shares, each stepped on its own
   // stream.  Members are independent, so the shares drift freely inside one af_net_step call
@@ -1694,6 +1943,85 @@ static cudaError_t launch_artery(const af_net* n, int ba0, int count, int inlet_
   return cudaLaunchKernelEx(&cfg, k_artery<T, false>, nd, n->cur, ba0, inlet_index, log_slot, gstep);
 }
 
+// persistent path: can all CTAs of k_artery_p and k_junction_p be resident together?  Registers and shared
+// memory per SM from the kernels' attributes; the artery CTAs are placed first (the hardware may spread them
+// over the SMs or fill SMs up -- both orders are tried), the junction CTAs must fit into what is left.
+template <int T>
+static bool persistent_fits(const af_net* n) {
+  // (kernel attributes and device properties are queried once per process and device: cudaGetDeviceProperties
+  // alone costs more than a millisecond, and networks are created in loops)
+  struct Info { bool ok; cudaFuncAttributes fa, fj; cudaDeviceProp prop; };
+  static std::mutex mu;
+  static std::map<int, Info> cache_;
+  Info info;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache_.find(n->device);
+    if (it == cache_.end()) {
+      Info q;
+      q.ok = cudaFuncGetAttributes(&q.fa, k_artery_p<T>) == cudaSuccess &&
+             cudaFuncGetAttributes(&q.fj, k_junction_p) == cudaSuccess &&
+             cudaGetDeviceProperties(&q.prop, n->device) == cudaSuccess;
+      if (!q.ok) cudaGetLastError();
+      it = cache_.insert({n->device, q}).first;
+    }
+    info = it->second;
+  }
+  if (!info.ok) return false;
+  const cudaFuncAttributes &fa = info.fa, &fj = info.fj;
+  const cudaDeviceProp& prop = info.prop;
+  auto warp_regs = [](int r) { return ((r * 32 + 255) / 256) * 256; };       // allocation unit: 256 registers per warp
+  const long long regs_a = (long long)warp_regs(fa.numRegs) * (T / 32), regs_j = (long long)warp_regs(fj.numRegs) * 4;
+  const long long smem_a = (long long)n->artery_smem + fa.sharedSizeBytes + 1024, smem_j = fj.sharedSizeBytes + 1024;
+  const long long R = prop.regsPerMultiprocessor, M = prop.sharedMemPerMultiprocessor;
+  const int nsm = prop.multiProcessorCount, thr = prop.maxThreadsPerMultiProcessor;
+  const int na = n->nd.na, ncj = (n->nd.nj + 3) / 4;
+  int per_sm = (int)std::min(R / regs_a, M / smem_a);
+  per_sm = std::min(per_sm, thr / T);
+  if (per_sm < 1 || (long long)per_sm * nsm < na) return false;
+  for (int order = 0; order < 2; ++order) {
+    std::vector<int> cnt(nsm, 0);
+    if (order == 0) for (int i = 0; i < na; ++i) cnt[i % nsm]++;                       // breadth first
+    else for (int i = 0, left = na; i < nsm && left > 0; ++i) { cnt[i] = std::min(per_sm, left); left -= cnt[i]; }
+    long long room = 0;
+    for (int i = 0; i < nsm; ++i) {
+      const long long rj = (R - cnt[i] * regs_a) / regs_j, mj = (M - cnt[i] * smem_a) / std::max(smem_j, 1LL);
+      const long long tj = (thr - cnt[i] * T) / 128;
+      room += std::max(0LL, std::min(rj, std::min(mj, tj)));
+    }
+    if (room < ncj) return false;
+  }
+  return true;
+}
+
+template <int T>
+static cudaError_t launch_persistent(const af_net* n, long long g0, int len, int log_slot0, int n_log) {
+  NetDev nd = n->nd;
+  k_artery_p<T><<<nd.na, T, n->artery_smem, n->stream>>>(nd, n->cur, g0, len, log_slot0, n_log);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || nd.nj == 0) return e;
+  // the junction kernel becomes resident beside the artery kernel (which triggers at its first instruction)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((nd.nj + 3) / 4));
+  cfg.blockDim = dim3(128);
+  cfg.stream = n->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_junction_p, nd, n->cur, g0, len, log_slot0, n_log);
+}
+
+static cudaError_t run_persistent(const af_net* n, long long g0, int len, int log_slot0, int n_log) {
+  switch (n->artery_threads) {
+    case 64: return launch_persistent<64>(n, g0, len, log_slot0, n_log);
+    case 128: return launch_persistent<128>(n, g0, len, log_slot0, n_log);
+    case 256: return launch_persistent<256>(n, g0, len, log_slot0, n_log);
+    default: return launch_persistent<512>(n, g0, len, log_slot0, n_log);
+  }
+}
+
 template <int T>
 static cudaError_t prepare_artery(af_net* n) {
   cudaError_t e = cudaFuncSetAttribute(k_artery<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1701,6 +2029,23 @@ static cudaError_t prepare_artery(af_net* n) {
   if (e == cudaSuccess && T >= 64)
     e = cudaFuncSetAttribute(k_artery<T, (T >= 64)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)n->artery_smem);
+  if (e == cudaSuccess && T >= 64 && n->nd.dataflow) {
+    e = cudaFuncSetAttribute(k_artery_p<(T >= 64 ? T : 64)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)n->artery_smem);
+    // persistent kernels over chunks of steps (AF_NO_PERSIST=1: one launch pair per step); every leaf must be
+    // a vessel the artery kernel knows as one, and all CTAs of both kernels must fit the device together
+    n->persist = e == cudaSuccess && n->pdl && persistent_fits<(T >= 64 ? T : 64)>(n);
+    if (const char* env = getenv("AF_NO_PERSIST")) if (atoi(env)) n->persist = false;
+    if (n->persist) {
+      // Both kernels run once, empty, while nothing else is resident: the first launch of a kernel may have
+      // to load its code (lazy module loading) and to grow the device's local-memory pool for its stack frame
+      // -- the driver does both only on an idle context, which a junction kernel launched NEXT TO a spinning
+      // artery kernel would wait for forever (measured: the arteries' mailbox polls ran into their time-out).
+      k_artery_p<(T >= 64 ? T : 64)><<<1, (T >= 64 ? T : 64), n->artery_smem, n->stream>>>(n->nd, 0, 0, 0, -1, 0);
+      k_junction_p<<<1, 128, 0, n->stream>>>(n->nd, 0, 0, 0, -1, 0);
+      e = cudaGetLastError();
+    }
+  }
   return e;
 }
 
@@ -2154,6 +2499,46 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_out, nba, (unsigned)n_first);
     k_fill_u64<<<(8 * nba + 127) / 128, 128, 0, n->stream>>>((unsigned long long*)n->nd.mbox, 8 * nba, AF_MBOX_EMPTY);
     AF_CUDA(cudaGetLastError());
+  }
+  if (n->persist && n->nd.dataflow && n_steps > 0) {
+    // chunks of up to kChunk steps; a chunk ends before a step whose Un is dumped (an:920-938: Un of t_n is
+    // stored BEFORE the solve of step n), so snapshots stay ordinary stream-ordered work between two chunks
+    const int64_t end = n_first + n_steps;
+    int64_t g = n_first;
+    while (g < end) {
+      if (n->fail_h && (g % af_net::kPoll) == 0) {        // same cadence as the per-step path below
+        if (n->fail_poll_pending && cudaEventQuery(n->fail_ev) == cudaSuccess) {
+          n->fail_poll_pending = false;
+          if (*n->fail_h != AF_NO_FAIL) n->failed = true;
+        }
+        if (n->failed) break;
+        if (!n->fail_poll_pending) {
+          AF_CUDA(cudaMemcpyAsync(n->fail_h, n->nd.fail_step, sizeof(unsigned long long), cudaMemcpyDeviceToHost, n->stream));
+          AF_CUDA(cudaEventRecord(n->fail_ev, n->stream));
+          n->fail_poll_pending = true;
+        }
+      }
+      auto dump_due = [&](int64_t gg) {
+        return n->max_snap && gg / Nt >= n->first_cycle && n->mask[(int)(gg % Nt)] && n->n_snap < n->max_snap;
+      };
+      if (dump_due(g)) {
+        rc = take_snapshot(n, g);
+        if (rc) return rc;
+      }
+      if (n->ring && n->n_delivered < n->n_streamed) {
+        rc = drain_ring(n, false, false);
+        if (rc) return rc;
+      }
+      int len = 1;                           // chunks end at multiples of kChunk (= kPoll: the failure poll above)
+      while ((g + len) % af_net::kChunk != 0 && g + len < end && !dump_due(g + len)) ++len;
+      const int n_log = std::max(0, std::min(len, n->log_cap - n->log_n));
+      const int log_slot0 = n_log > 0 ? n->log_n : -1;
+      n->log_n += n_log;
+      AF_CUDA(run_persistent(n, g, len, log_slot0, n_log));
+      n->cur ^= (len & 1);
+      g += len;
+    }
+    return AF_OK;
   }
   const bool split = n->n_sub > 1 && n_steps > 0;
   if (split && (rc = fork_subs(n))) return rc;

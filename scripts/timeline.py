@@ -116,3 +116,10 @@ for g in range(8):
           'resident before own previous release: %.0f %%'
           % (g, us(art[1:, sel, 0] - art[:-1, sel, 7]), us(art[:, sel, 3] - art[:, sel, 2]),
              100.0 * np.mean(art[1:, sel, 0] < art[:-1, sel, 7])))
+
+# junction Newton: stamps at the top of iterations 1 and 2 (slots 5, 6) and the iteration count at exit (slot 7)
+k_exit = jun[:, :, 7]
+print('junction Newton exits after k linearisations: histogram', np.bincount(k_exit.flatten().clip(0, 31))[:8].tolist())
+ok = (jun[:, :, 5] > 0) & (jun[:, :, 6] > 0)
+print('junction: set-up done -> top of iteration 1: %.2f us; iteration 1 -> 2: %.2f us'
+      % (us((jun[:, :, 5] - jun[:, :, 2])[jun[:, :, 5] > 0]), us((jun[:, :, 6] - jun[:, :, 5])[ok])))

@@ -127,8 +127,8 @@ import bloodflow_b200.arteryfe as af
 from bloodflow_b200 import ensemble as en
 from bloodflow_b200.synthetic import tree_param
 out = {}
-for name, p, steps in (('c1', af.ParamParser('tests/golden/golden_c1.cfg'), 120),
-                       ('o3', af.ParamParser('tests/golden/golden_o3.cfg'), 120),
+for name, p, steps in (('c1', af.ParamParser('tests/golden/golden_c1.cfg'), 200),      # > one 64-step chunk per call
+                       ('o3', af.ParamParser('tests/golden/golden_o3.cfg'), 200),
                        ('c4', tree_param(8, Nx=1000, Nt=8000), 40)):
     an = af.ArteryNetwork(p)
     an.define_x()
@@ -151,16 +151,19 @@ np.savez(sys.argv[1], **out)
 
 
 def test_plain_stream_order_equals_programmatic_dependent_launch(tmp_path):
-    """The default scheduling (programmatic dependent launch + per-artery / per-junction dataflow flags
-    on multi-warp single networks) against AF_NO_DATAFLOW=1 (dependent launch with grid-wide waits) and
-    AF_NO_PDL=1 (plain stream order between the two kernels of a step): state, junction unknowns, Dirichlet data, dex and every counter
+    """The default scheduling of multi-warp single networks (persistent kernels over chunks of steps,
+    per-artery flags, Dirichlet mailbox, leaves' Windkessel inside their artery CTA) against AF_NO_PERSIST=1
+    (one launch pair per step with the same flags and mailbox), AF_NO_DATAFLOW=1 (dependent launch with
+    grid-wide waits) and AF_NO_PDL=1 (plain stream order between the two kernels of a step): state,
+    junction unknowns, Dirichlet data, dex and every counter
     bitwise equal on the demo bifurcation, the order-3 tree, a short run of the order-8 tree and a
     700-member ensemble.  Guards the 'only constants before the grid-dependency wait' rule of
     k_boundary / k_artery (af_kernels.cu)."""
     script = tmp_path / 'pdl_worker.py'
     script.write_text(PDL_WORKER % {'root': ROOT})
     outs = []
-    for tag, env in (('default', {}), ('no_dataflow', {'AF_NO_DATAFLOW': '1'}), ('plain', {'AF_NO_PDL': '1'})):
+    for tag, env in (('default', {}), ('no_persist', {'AF_NO_PERSIST': '1'}), ('no_dataflow', {'AF_NO_DATAFLOW': '1'}),
+                     ('plain', {'AF_NO_PDL': '1'})):
         path = str(tmp_path / (tag + '.npz'))
         r = subprocess.run([sys.executable, str(script), path], env=dict(os.environ, **env), capture_output=True,
                            text=True, timeout=900)
