@@ -17,6 +17,7 @@ AF_OK, AF_EINVAL, AF_ENODEVICE, AF_ECUDA, AF_ENOMEM, AF_ESTATE = 0, -1, -2, -3, 
 AF_FLAG_ARTERY_NOCONV, AF_FLAG_JUNCTION_KMAX, AF_FLAG_PICARD_KMAX = 1, 2, 4
 AF_FLAG_NONFINITE, AF_FLAG_SINGULAR, AF_FLAG_PICARD_CYCLE, AF_FLAG_SYNC_TIMEOUT = 8, 16, 32, 64
 AF_STORE_FLOW, AF_STORE_AREA, AF_STORE_PRESSURE, AF_STORE_OUTLET_PRESSURE = 1, 2, 4, 8
+AF_SCHEDULE_PER_STEP, AF_SCHEDULE_DATAFLOW, AF_SCHEDULE_PERSISTENT, AF_SCHEDULE_FUSED = 0, 1, 2, 3
 
 c_int, c_i32, c_i64, c_dbl = ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 P_dbl = ctypes.POINTER(ctypes.c_double)
@@ -55,6 +56,7 @@ PROTOTYPES = {
     'af_net_step': (c_int, [Handle, c_i64, c_i64]),
     'af_net_sync': (c_int, [Handle]),
     'af_net_failed_step': (c_int, [Handle, P_i64]),
+    'af_net_schedule': (c_int, [Handle, P_i32]),
     'af_net_clear_flags': (c_int, [Handle]),
     'af_net_outlet_moments_d': (c_int, [Handle, ctypes.POINTER(ctypes.c_void_p), P_i32]),
     'af_moments_combine_d': (c_int, [c_i32, ctypes.c_void_p, ctypes.c_void_p, c_i32, c_i32, ctypes.c_void_p]),

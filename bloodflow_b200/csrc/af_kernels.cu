@@ -168,6 +168,7 @@ struct NetDev {
   unsigned* f_in;
   unsigned* f_out;
   double* mbox;                   // [2][nb*na*4] Dirichlet mailbox, slot set = parity of the time step
+  const int* art_perm;            // persistent artery kernel: artery of CTA blockIdx.x (nullptr: identity)
   int dataflow;
 #ifdef AF_TIMELINE
   // debug builds only (make timeline): %globaltimer stamps of the last tl_steps steps,
@@ -353,7 +354,8 @@ __device__ __forceinline__ void junction_task(const NetDev& nd, int cur, int b, 
 // so the boundary kernel fetches them before its grid-dependency wait.
 __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, int b, int j, const int* ia,
                                                     const Vessel& ves, const double* xg, double* x, double& dex,
-                                                    int& solves, uint32_t& fl, long long tl_g = -1) {
+                                                    int& solves, uint32_t& fl, bool& singular_out,
+                                                    long long tl_g = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int v = lane % 3;
@@ -416,16 +418,10 @@ __device__ __forceinline__ void junction_solve_warp(const NetDev& nd, int cur, i
   if (lane == 0 && nd.tl && tl_g >= 0)
     nd.tl[((tl_g % nd.tl_steps) * (size_t)(nd.na + nd.nj + nd.nl) + nd.na + j) * 8 + 7] = (unsigned long long)k;
 #endif
-  if (singular) {               // warp-uniform; the verbatim dense path owns the reference's singular branch
-    // (through copies: handing x itself to the out-of-line routine would make it addressable and put the
-    // 18 unknowns into local memory for the whole Newton loop above)
-    double xs[18];
-    uint32_t fls = 0;
-    for (int i = 0; i < 18; ++i) xs[i] = xg[i];
-    solves = junction_slow_path(nd, cur, b, ia, dex, xs, &fls);
-    for (int i = 0; i < 18; ++i) x[i] = xs[i];
-    fl = fls;
-  }
+  // a vanished 3x3 pivot (warp-uniform): the caller re-runs the step on the verbatim dense path, which owns the
+  // reference's singular branch -- on arrays of its own, so that x above never becomes addressable (it would
+  // live in local memory for the whole Newton loop) and is not merged with them through memory afterwards
+  singular_out = singular;
 }
 
 __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, int b, int j, const int* ia,
@@ -434,11 +430,19 @@ __device__ __forceinline__ void junction_task_warp(const NetDev& nd, int cur, in
   int solves;
   uint32_t fl;
   const double* xg = nd.jx + ((size_t)b * nd.nj + j) * 18;
-  junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl, flag_step);
-  // (an if-block, not an early return: inside the step loop of k_junction_p the warp must be converged
-  // again afterwards -- with lane 0 on a path of its own every __shfl_sync of the next step took its
-  // divergent slow path and a Newton iteration cost 7.5 us instead of 0.9 us)
-  if ((threadIdx.x & 31) == 0) junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot, flag_step);
+  bool singular;
+  junction_solve_warp(nd, cur, b, j, ia, ves, xg, x, dex, solves, fl, singular, flag_step);
+  // (if-blocks, not an early return: inside the step loop of k_junction_p the warp must be converged
+  // again afterwards)
+  if (!singular) {
+    if ((threadIdx.x & 31) == 0) junction_finish(nd, b, j, ia, x, dex, solves, fl, log_slot, flag_step);
+  } else {
+    double xs[18];
+    uint32_t fls = 0;
+    for (int i = 0; i < 18; ++i) xs[i] = xg[i];
+    const int s2 = junction_slow_path(nd, cur, b, ia, dex, xs, &fls);
+    if ((threadIdx.x & 31) == 0) junction_finish(nd, b, j, ia, xs, dex, s2, fls, log_slot, flag_step);
+  }
   __syncwarp();
 }
 
@@ -1061,7 +1065,14 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
         uint32_t jfl;
         const int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
         const Vessel jves = nd.ves[b * nd.na + ia[lane % 3]];
-        junction_solve_warp(nd, cur, b, j, ia, jves, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
+        bool sing;
+        junction_solve_warp(nd, cur, b, j, ia, jves, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl, sing);
+        if (sing) {             // verbatim dense path (reference's singular branch)
+          const double* xg0 = nd.jx + ((size_t)b * nd.nj + j) * 18;
+          for (int i = 0; i < 18; ++i) x[i] = xg0[i];
+          jfl = 0;
+          solves = junction_slow_path(nd, cur, b, ia, dex, x, &jfl);
+        }
         if (lane == 0) {
           const bool first_daughter = nd.art_role[a] == 1;
           bcv[0] = first_daughter ? x[12] : x[15];
@@ -1079,7 +1090,14 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
         uint32_t jfl;
         const int ia[3] = {nd.j_p[j], nd.j_d1[j], nd.j_d2[j]};
         const Vessel jves = nd.ves[b * nd.na + ia[lane % 3]];
-        junction_solve_warp(nd, cur, b, j, ia, jves, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl);
+        bool sing;
+        junction_solve_warp(nd, cur, b, j, ia, jves, nd.jx + ((size_t)b * nd.nj + j) * 18, x, dex, solves, jfl, sing);
+        if (sing) {             // verbatim dense path (reference's singular branch)
+          const double* xg0 = nd.jx + ((size_t)b * nd.nj + j) * 18;
+          for (int i = 0; i < 18; ++i) x[i] = xg0[i];
+          jfl = 0;
+          solves = junction_slow_path(nd, cur, b, ia, dex, x, &jfl);
+        }
         if (lane == 0) {
           bcv[2] = x[9]; bcv[3] = x[0];
           double* xo = nd.jx_next + ((size_t)b * nd.nj + j) * 18;
@@ -1237,7 +1255,7 @@ k_artery_p(NetDev nd, int cur, long long g0, int n_steps, int log_slot0, int n_l
   double* pc = pb + 10 * T;
   // the junction kernel of this chunk follows in the stream as a programmatic dependent launch
   cudaTriggerProgrammaticLaunchCompletion();
-  const int ba = blockIdx.x, b = 0, a = ba;
+  const int ba = nd.art_perm ? nd.art_perm[blockIdx.x] : blockIdx.x, b = 0, a = ba;
   const Vessel v = nd.ves[ba];
   const size_t off = (size_t)ba * S;
   {
@@ -2037,6 +2055,23 @@ static cudaError_t prepare_artery(af_net* n) {
     n->persist = e == cudaSuccess && n->pdl && persistent_fits<(T >= 64 ? T : 64)>(n);
     if (const char* env = getenv("AF_NO_PERSIST")) if (atoi(env)) n->persist = false;
     if (n->persist) {
+      // CTAs are handed to the SMs round-robin: with na CTAs on nsm SMs (nsm < na <= 2 nsm) the CTAs
+      // na - nsm .. nsm - 1 keep an SM to themselves.  Those go to the upper generations of the tree (arteries are
+      // numbered generation by generation): the root <-> first-junction cycle sets the period of the whole
+      // network, and a CTA that shares neither the FP64 pipe nor the shared-memory bandwidth runs its Newton
+      // passes faster (AF_NO_SOLO=1 keeps the identity mapping).
+      int nsm = 0;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, n->device);
+      const int na = n->nd.na;
+      const char* env = getenv("AF_NO_SOLO");
+      if (nsm > 0 && na > nsm && na <= 2 * nsm && !(env && atoi(env))) {
+        std::vector<int> perm(na);
+        const int lo = na - nsm, hi = nsm;          // solo CTAs: [lo, hi)
+        int next_upper = 0, next_rest = hi - lo;
+        for (int bi = 0; bi < na; ++bi) perm[bi] = (bi >= lo && bi < hi) ? next_upper++ : next_rest++;
+        int* dperm = nullptr;
+        if (n->upload(&dperm, perm.data(), (size_t)na) == AF_OK) n->nd.art_perm = dperm;
+      }
       // Both kernels run once, empty, while nothing else is resident: the first launch of a kernel may have
       // to load its code (lazy module loading) and to grow the device's local-memory pool for its stack frame
       // -- the driver does both only on an idle context, which a junction kernel launched NEXT TO a spinning
@@ -2354,6 +2389,14 @@ extern "C" int af_net_debug_timeline(af_net* n, unsigned long long* out, int64_t
   return AF_OK;
 }
 #endif
+
+extern "C" int af_net_schedule(af_net* n, int32_t* kind) {
+  if (!n || !kind) return fail(AF_EINVAL, "null argument");
+  *kind = n->fused ? AF_SCHEDULE_FUSED
+                   : (n->persist && n->nd.dataflow ? AF_SCHEDULE_PERSISTENT
+                                                   : (n->nd.dataflow ? AF_SCHEDULE_DATAFLOW : AF_SCHEDULE_PER_STEP));
+  return AF_OK;
+}
 
 extern "C" int af_net_sync(af_net* n) {
   int rc = check(n);

@@ -111,6 +111,12 @@ class DeviceNetwork(object):
     def clear_flags(self):
         check(lib.af_net_clear_flags(self._h))
 
+    def schedule(self):
+        """How af_net_step runs the loop on this handle (_ffi.AF_SCHEDULE_*)."""
+        k = ctypes.c_int32(0)
+        check(lib.af_net_schedule(self._h, ctypes.byref(k)))
+        return k.value
+
     def outlet_moments_device(self):
         """(device pointer, n_snapshots) of the packed moments [5][n_snapshots*n_leaves] of the stored
         outlet pressures over this handle's members (count, sum, sum of squares, min, max)."""

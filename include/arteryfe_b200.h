@@ -150,6 +150,18 @@ int af_net_step(af_net* net, int64_t n_first, int64_t n_steps);
 int af_net_failed_step(af_net* net, int64_t* step);
 /* Reset the status bits and the failed step (they are sticky otherwise). */
 int af_net_clear_flags(af_net* net);
+/* How af_net_step schedules the loop body of artery_network.py:908-946 on this handle (chosen at creation from
+ * the network's shape, the device and the AF_* environment knobs; results are bitwise the same for all):
+ *   AF_SCHEDULE_PER_STEP      two launches per time step, ordered by grid-wide waits (ensembles; AF_NO_DATAFLOW=1)
+ *   AF_SCHEDULE_DATAFLOW      two launches per time step, ordered by per-artery flags and the Dirichlet mailbox
+ *   AF_SCHEDULE_PERSISTENT    one launch pair per chunk of up to 64 time steps (single networks whose kernels fit
+ *                             the device together)
+ *   AF_SCHEDULE_FUSED         one launch per time step, boundary update inside the artery CTAs (AF_FUSE=1) */
+#define AF_SCHEDULE_PER_STEP 0
+#define AF_SCHEDULE_DATAFLOW 1
+#define AF_SCHEDULE_PERSISTENT 2
+#define AF_SCHEDULE_FUSED 3
+int af_net_schedule(af_net* net, int32_t* kind);
 
 /* Wait for everything enqueued on the handle's stream. */
 int af_net_sync(af_net* net);
