@@ -442,6 +442,7 @@ def main():
     stream = torch.cuda.Stream(device=local_rank)
     an = af.ArteryNetwork(p, device=local_rank, stream=stream.cuda_stream)
     dev = an._dev
+    schedule = dev.schedule()
     nodes = dev.na * dev.np
     an.define_x()
     mask = an.store_mask()
@@ -526,7 +527,6 @@ def main():
         peaks, peak_kind = measured_peaks()
         peak_tf = fp64_peak(local_rank)
         ms_step = ms_total / K
-        schedule = dev.schedule()
         n_launches, n_dumps, n_art_launches = launches_in(schedule, W, K, args.Nt, mask)
         if schedule == _ffi.AF_SCHEDULE_PERSISTENT:
             # the artery kernel is persistent: a launch lives for its whole chunk of time steps (the junction

@@ -8,7 +8,7 @@ import bloodflow_b200.arteryfe as af                       # noqa: E402
 from bloodflow_b200.ensemble import perturb_param          # noqa: E402
 from bloodflow_b200.synthetic import tree_param            # noqa: E402
 
-K = 2000
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 for m in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     p = tree_param(8, Nx=1000, Nt=8000)
     if m:
