@@ -7,10 +7,14 @@
 //   bc[nb*na*4]                    A_in, q_in, A_out, q_out   (the reference's BC holders)
 //   dex[nb*na], jx[nb*nj*18]       boundary step, junction unknowns (warm start)
 //   cellcoef[nt][9][S]             Gauss-point coefficients, tapered arteries only
-// One launch of k_boundary (all junctions + leaves of all networks) and one of
-// k_artery (one CTA per artery) make a time step; the two are chained by
-// programmatic dependent launch in both directions.  Large ensembles are cut into
-// member shares that run this chain on their own forked streams (af_net_step).
+//   f_art[nb*na], f_out[nb*na]     release/acquire flags (completed steps per artery / junction)
+//   mbox[2][nb*na*4]               Dirichlet mailbox junction -> artery (data = flag), by step parity
+// Ensembles: one launch of k_boundary (all junctions + leaves of all networks) and one of
+// k_artery (one CTA per artery) make a time step, chained by programmatic dependent launch
+// in both directions; large ensembles are cut into member shares that run this chain on
+// their own forked streams.  Single networks: the persistent pair k_artery_p / k_junction_p
+// advances a chunk of time steps per launch, ordered by the flags and the mailbox alone
+// (or, AF_NO_PERSIST=1, the same two per-step kernels with those flags).  af_net_step picks.
 // Host side: the C ABI, a pinned ring that streams snapshots out during the loop,
 // and an exact-size cache of released device / pinned blocks.  See DESIGN.md.
 #include <cuda_runtime.h>
