@@ -467,25 +467,41 @@ __device__ __forceinline__ void leaf_task(const NetDev& nd, int cur, int b, int 
 // one warp per leaf (single networks): lanes 0..2 take the three stencil points
 // L-2dex, L-dex, L of windkessel() (an:383-390), lanes 0..1 the two half steps
 // (an:393-398); the Picard loop is inherently serial.
-__device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, int b, int l, int ba,
-                                                    const Vessel& ves, int log_slot, long long flag_step = -1) {
+// P1 interpolation of the state (interp_state) with the vertex index mapped: TS = 0, vertex i at [i] (Un in
+// global memory); TS > 0, vertex i at [(i & 3) * TS + (i >> 2)] (the iterate of a TS-thread artery CTA in
+// shared memory, see vix).  Same arithmetic, same order.
+template <int TS>
+__device__ __forceinline__ void interp_state_mapped(const double* A, const double* q, int Nx, double dx, double x,
+                                                    double& Ax, double& qx) {
+  const double inv_dx = af_rcp_fast(dx);
+  int j = (int)floor(x * inv_dx);
+  j = j < 0 ? 0 : (j > Nx - 1 ? Nx - 1 : j);
+  double xi = (x - j * dx) * inv_dx;
+  const int j0 = TS ? (j & 3) * TS + (j >> 2) : j, j1 = TS ? ((j + 1) & 3) * TS + ((j + 1) >> 2) : j + 1;
+  Ax = A[j0] * (1.0 - xi) + A[j1] * xi;
+  qx = q[j0] * (1.0 - xi) + q[j1] * xi;
+}
+
+// `A`, `q`: Un of the leaf artery -- in global memory (TS = 0: nd.A[cur] + ba * S) or, inside the persistent
+// artery kernel, the CTA's own iterate in shared memory (TS = its thread count), which holds the same values
+// two L2 round trips closer.
+template <int TS = 0>
+__device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, const double* A, const double* q, int b, int l,
+                                                    int ba, const Vessel& ves, int log_slot, long long flag_step = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = lane % 3;
-  const size_t off = (size_t)ba * nd.S;
-  const double* A = nd.A[cur] + off;
-  const double* q = nd.q[cur] + off;
   const double L = ves.L, dt = nd.dt;
   // adjust_dex (ar:349-365)
   Coef cL;
   cL.f = ves.fL; cL.A0 = ves.A0L;
   double AL, qL;
-  interp_state(A, q, nd.Nx, ves.dx, L, AL, qL);
+  interp_state_mapped<TS>(A, q, nd.Nx, ves.dx, L, AL, qL);
   const double dex = AF_DIV((1.0 + nd.cfl_margin) * dt, cfl_term(ves, cL, AL, qL));
   // stencil point of this lane and its flux / source (an:385-390)
   const double xk = L - (double)(2 - k) * dex;
   double Ak, qk;
-  interp_state(A, q, nd.Nx, ves.dx, xk, Ak, qk);
+  interp_state_mapped<TS>(A, q, nd.Nx, ves.dx, xk, Ak, qk);
   const Coef ck = coef_at(ves, xk);
   const double Fk = bc_flux2(ck, Ak, qk), Sk = bc_source2(ves, ck, Ak, qk);
   // half step between this point and the next one (compute_U_half, an:393-394)
@@ -506,21 +522,24 @@ __device__ __forceinline__ WkResult leaf_solve_warp(const NetDev& nd, int cur, i
   const double qm1 = q1 - AF_DIV(dt, dex) * (F10 - F21) + dt / 2.0 * (S10 + S21);
   WkResult r;
   r.A_out = 0.0; r.dex = dex; r.its = 0; r.cycle = 0;
-  if (lane != 0) return r;
-  AF_TL(nd, flag_step, nd.na + nd.nj + l, 2);
-  const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
-  r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
-  AF_TL(nd, flag_step, nd.na + nd.nj + l, 3);
-  if (flag_step >= 0)      // dataflow: A_out (an:786) into the mailbox slot of the outlet (see junction_finish)
-    mbox_put(&nd.mbox[(size_t)(flag_step & 1) * nd.nb * nd.na * 4 + ba * 4 + 2], r.A_out);
-  else
-    nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
-  nd.dex[ba] = r.dex;
-  AF_TL(nd, flag_step, nd.na + nd.nj + l, 4);
-  nd.picard_its[b * nd.nl + l] = r.its;
-  if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
-  atomicAdd(&nd.totals[2], (unsigned long long)r.its);
-  if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)(r.cycle ? AF_FLAG_PICARD_CYCLE : AF_FLAG_PICARD_KMAX));
+  // (an if-block, not an early return of the other lanes: the warp goes on together afterwards, see junction_task_warp)
+  if (lane == 0) {
+    AF_TL(nd, flag_step, nd.na + nd.nj + l, 2);
+    const double* w = nd.wk + ((size_t)b * nd.nl + l) * 3;
+    r = windkessel_picard(ves, dt, dex, A0s, q0s, qm1, w[0], w[1], w[2], nd.picard_k_max, nd.picard_tol);
+    AF_TL(nd, flag_step, nd.na + nd.nj + l, 3);
+    if (flag_step >= 0)      // dataflow: A_out (an:786) into the mailbox slot of the outlet (see junction_finish)
+      mbox_put(&nd.mbox[(size_t)(flag_step & 1) * nd.nb * nd.na * 4 + ba * 4 + 2], r.A_out);
+    else
+      nd.bc[ba * 4 + 2] = r.A_out;       // A_out (an:786)
+    nd.dex[ba] = r.dex;
+    AF_TL(nd, flag_step, nd.na + nd.nj + l, 4);
+    nd.picard_its[b * nd.nl + l] = r.its;
+    if (log_slot >= 0) nd.log_p[(size_t)log_slot * nd.nb * nd.nl + b * nd.nl + l] = r.its;
+    atomicAdd(&nd.totals[2], (unsigned long long)r.its);
+    if (r.its >= nd.picard_k_max) atomicOr(&nd.flags[b], (uint32_t)(r.cycle ? AF_FLAG_PICARD_CYCLE : AF_FLAG_PICARD_KMAX));
+  }
+  __syncwarp();
   return r;
 }
 
@@ -594,7 +613,7 @@ __global__ void k_boundary(NetDev nd, int cur, int log_slot, int b0, int nbl, lo
     if (is_junction)
       junction_task_warp(nd, cur, b, j, ia, ves, log_slot, flag_step);
     else if (is_leaf)
-      leaf_solve_warp(nd, cur, b, l, ba, ves, log_slot, flag_step);
+      leaf_solve_warp(nd, nd.A[cur] + (size_t)ba * nd.S, nd.q[cur] + (size_t)ba * nd.S, b, l, ba, ves, log_slot, flag_step);
   } else {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
@@ -1085,7 +1104,7 @@ k_artery(NetDev nd, int cur, int ba0, int inlet_index, int log_slot, long long g
       }
     } else if (w == 1) {
       if (c.leaf) {
-        WkResult r = leaf_solve_warp(nd, cur, b, nd.art_leaf[a], ba, v, log_slot);   // writes bc/dex/counters itself
+        WkResult r = leaf_solve_warp(nd, nd.A[cur] + off, nd.q[cur] + off, b, nd.art_leaf[a], ba, v, log_slot);   // writes bc/dex/counters itself
         if (lane == 0) { bcv[2] = r.A_out; bcv[3] = nd.bc[ba * 4 + 3]; }
       } else {
         const int j = nd.art_jout[a];
@@ -1313,9 +1332,9 @@ k_artery_p(NetDev nd, int cur, long long g0, int n_steps, int log_slot0, int n_l
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
     }
     if (c.leaf && (tid >> 5) == 1) {
-      // set_bcs of a leaf (an:780-786): its Windkessel needs nothing but this artery's own Un, which this
-      // CTA wrote (and published with a barrier) at the end of the previous step
-      WkResult r = leaf_solve_warp(nd, cur, b, nd.art_leaf[a], ba, v, log_slot, -1);
+      // set_bcs of a leaf (an:780-786): its Windkessel needs nothing but this artery's own Un, which is the
+      // iterate this CTA holds in shared memory (U == Un between two steps)
+      WkResult r = leaf_solve_warp<T>(nd, sA, sq, b, nd.art_leaf[a], ba, v, log_slot, -1);
       if ((tid & 31) == 0) bcv[2] = r.A_out;
     }
     uint32_t fl = 0;

@@ -1,7 +1,7 @@
 """Per-task %globaltimer timeline of the order-8 tree's time loop (debug build of the library).
 
     make -C bloodflow_b200/csrc timeline
-    ARTERYFE_B200_LIB=bloodflow_b200/csrc/libarteryfe_b200_tl.so AF_TIMELINE_STEPS=64 python scripts/timeline.py [K] [theta]
+    ARTERYFE_B200_LIB=bloodflow_b200/csrc/libarteryfe_b200_tl.so AF_TIMELINE_STEPS=64 python scripts/timeline.py [K] [theta] [member]
 
 Stamps (ns): artery 0 start, 1 own flag seen, 2 first-pass cells done, 3 Dirichlet flags seen, 4 first norm,
 5 last solve + update done, 6 converged, 7 released; junction / leaf 0 start, 1 flags seen, 2 set-up done,
@@ -21,7 +21,12 @@ from bloodflow_b200.synthetic import tree_param           # noqa: E402
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 theta = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6
 NS = int(os.environ.get('AF_TIMELINE_STEPS', '64'))
-an = af.ArteryNetwork(tree_param(8, Nx=1000, Nt=8000, theta=theta))
+member = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+_p = tree_param(8, Nx=1000, Nt=8000, theta=theta)
+if member:
+    from bloodflow_b200.ensemble import perturb_param
+    _p = perturb_param(_p, member)
+an = af.ArteryNetwork(_p)
 an.define_x()
 dev = an._dev
 K = (K // NS) * NS
