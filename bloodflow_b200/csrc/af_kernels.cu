@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <new>
@@ -2551,6 +2552,30 @@ static int join_subs(af_net* n) {
   return AF_OK;
 }
 
+// One persistent kernel pair per device at a time (per process): two pairs at once could each hold part of the
+// SMs and wait for CTAs that never become resident.  af_net_step takes the lease for the work it enqueues and a
+// host function at the end of that work gives it back; a call that finds the lease taken simply uses the
+// per-step launches (same results), e.g. two networks stepped concurrently from two threads.
+// (Calls on the handle that already holds it share the lease: back-to-back af_net_step calls stay persistent.)
+struct PersistLease {
+  std::mutex mu;
+  const af_net* owner = nullptr;
+  int count = 0;
+  bool acquire(const af_net* n) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (count > 0 && owner != n) return false;
+    owner = n;
+    ++count;
+    return true;
+  }
+  void release() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (count > 0 && --count == 0) owner = nullptr;
+  }
+};
+static PersistLease g_persist_lease[64];
+static void CUDART_CB persist_release(void* p) { static_cast<PersistLease*>(p)->release(); }
+
 extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
   int rc = check(n);
   if (rc) return rc;
@@ -2566,7 +2591,16 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     k_fill_u64<<<(8 * nba + 127) / 128, 128, 0, n->stream>>>((unsigned long long*)n->nd.mbox, 8 * nba, AF_MBOX_EMPTY);
     AF_CUDA(cudaGetLastError());
   }
-  if (n->persist && n->nd.dataflow && n_steps > 0) {
+  PersistLease* lease = nullptr;
+  if (n->persist && n->nd.dataflow && n_steps > 0 && n->device >= 0 && n->device < 64 &&
+      g_persist_lease[n->device].acquire(n))
+    lease = &g_persist_lease[n->device];
+  if (lease) {
+    // given back when the stream has run everything enqueued below (also on an error return)
+    struct Release {
+      PersistLease* l; cudaStream_t s;
+      ~Release() { if (cudaLaunchHostFunc(s, persist_release, l) != cudaSuccess) { cudaGetLastError(); l->release(); } }
+    } release{lease, n->stream};
     // chunks of up to kChunk steps; a chunk ends before a step whose Un is dumped (an:920-938: Un of t_n is
     // stored BEFORE the solve of step n), so snapshots stay ordinary stream-ordered work between two chunks
     const int64_t end = n_first + n_steps;

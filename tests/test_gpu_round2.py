@@ -284,3 +284,35 @@ def test_c5_members_over_both_cycles_match_c_oracle():
         assert np.count_nonzero(jun[:, m] != lj) <= 1e-3 * lj.size and np.abs(jun[:, m] - lj).max() <= 1
         c.close()
     assert ens.flagged_members() == 0
+
+
+def test_two_networks_stepped_concurrently_share_the_device():
+    """The persistent kernel pair of a single network needs all of its CTAs resident; two pairs at once could
+    starve each other.  af_net_step therefore takes a per-device lease, and a call that finds it taken uses the
+    per-step launches (same results).  Two order-6 trees stepped from two threads at the same time: both
+    finish without a wait time-out and equal a network stepped alone, bit for bit."""
+    import threading
+    import bloodflow_b200.arteryfe as af
+    from bloodflow_b200 import _ffi
+    from bloodflow_b200.synthetic import tree_param
+
+    def make():
+        an = af.ArteryNetwork(tree_param(6, Nx=500, Nt=4000))
+        an.define_x()
+        return an
+
+    alone = make()
+    assert alone._dev.schedule() == _ffi.AF_SCHEDULE_PERSISTENT
+    alone._dev.step(0, 600)
+    A0, q0 = alone._dev.get_state()
+    nets = [make(), make()]
+    threads = [threading.Thread(target=lambda a=a: [a._dev.step(k * 100, 100) for k in range(6)]) for a in nets]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for an in nets:
+        A, q = an._dev.get_state()
+        assert int(an._dev.get_flags()[0]) & (1 | 8 | 64) == 0          # no failure, no AF_FLAG_SYNC_TIMEOUT
+        np.testing.assert_array_equal(A, A0)
+        np.testing.assert_array_equal(q, q0)
