@@ -7,8 +7,9 @@
 Headline workload (BASELINE.json config 4, the one the 1e9 target is quoted on): the
 synthetic order-8 tree, 255 arteries x 1001 vertices, Nt = 8000 steps per cardiac cycle,
 Windkessel outlets on the 128 leaves, data/example_inlet.csv.  A "step" is one time step
-of the whole network (set_bcs + every artery solve).  N GPUs: N parameter-perturbed
-order-8 trees, one per GPU (weak scaling; a single network does not shard).
+of the whole network (set_bcs + every artery solve).  N GPUs: N replicas of that tree, one
+per GPU (weak scaling; a single network does not shard; --tree-members perturbed runs N
+parameter-perturbed members instead, whose costs differ).
 
 The same JSON line carries `ensemble_c5`: BASELINE.json config 5, 65 536 perturbed order-4
 networks SHARDED over the N GPUs (strong scaling), exactly its two cardiac cycles, the
@@ -183,7 +184,7 @@ def run_reference(args, rank, world):
     budget = 150.0 / n_members
     total_nodes_steps, total_s, failed, K_run = 0.0, 0.0, 0, K
     for m in range(n_members):
-        c = _c_oracle(args.order, args.Nx, args.Nt, m, args.theta)
+        c = _c_oracle(args.order, args.Nx, args.Nt, member_of(args, m), args.theta)
         nodes = c.na * c.np
         t0 = time.perf_counter()
         c.step(0, max(W, 1), nthreads=cores)
@@ -196,7 +197,7 @@ def run_reference(args, rank, world):
         total_s += dt
         c.close()
     value = total_nodes_steps / total_s
-    sample = ("%d of the requested %d time steps of each of the %d order-%d tree member(s) the GPU arm runs, "
+    sample = ("%d of the requested %d time steps of each of the %d order-%d tree(s) the GPU arm runs, "
               "one after the other (bounded sample), oracle/oracle.c, OpenMP %d threads"
               % (K_run, K, n_members, args.order, cores))
     line = {
@@ -213,11 +214,21 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def member_of(args, rank):
+    """Which member of the tree ensemble GPU `rank` runs: the nominal tree everywhere (replicas: a single
+    network does not shard, so N GPUs measure N independent copies of the same work), or -- `--tree-members
+    perturbed` -- member `rank` of the UQ ensemble around it (members then differ in cost by up to 16 %,
+    profiles/r02_final_member_cost_*.log, and the slowest sets the line)."""
+    return rank if args.tree_members == 'perturbed' else 0
+
+
 def workload_config(args):
     return {"workload": "synthetic symmetric tree order=%d (%d arteries x %d vertices), Nt=%d per cycle, "
-                        "Windkessel outlets on %d leaves, data/example_inlet.csv; N GPUs = N perturbed "
-                        "members, one per GPU" % (args.order, 2 ** args.order - 1, args.Nx + 1, args.Nt,
-                                                  2 ** (args.order - 1)),
+                        "Windkessel outlets on %d leaves, data/example_inlet.csv; N GPUs = %s, one per GPU (a single "
+                        "network does not shard; the sharded workload is ensemble_c5)"
+                        % (args.order, 2 ** args.order - 1, args.Nx + 1, args.Nt, 2 ** (args.order - 1),
+                           "N perturbed members of the tree ensemble" if args.tree_members == 'perturbed'
+                           else "N replicas of this tree"),
             "order": args.order, "Nx": args.Nx, "Nt": args.Nt, "theta": args.theta,
             "l2": "no flush: the time loop is a dependent chain (step n+1 reads exactly what step n wrote), so "
                   "L2 residency of the %.1f MB state is the real operating point; nothing is cached or skipped "
@@ -269,7 +280,7 @@ def launches_in(dev_schedule, W, K, Nt, mask, chunk=64):
 def end_to_end(args, rank, local_rank, K):
     import bloodflow_b200.arteryfe as af
     n_cycles = -(-K // args.Nt)
-    p = tree_member(args.order, args.Nx, args.Nt, rank, N_cycles=n_cycles, theta=args.theta)
+    p = tree_member(args.order, args.Nx, args.Nt, member_of(args, rank), N_cycles=n_cycles, theta=args.theta)
     p.solution['N_cycles_store'] = n_cycles          # snapshots from the first step on
     t0 = time.perf_counter()
     an = af.ArteryNetwork(p, device=local_rank)
@@ -409,6 +420,8 @@ def main():
     ap.add_argument('--theta', type=float, default=THETA)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c5', action='store_true', help='skip the ensemble_c5 record')
+    ap.add_argument('--tree-members', choices=('replicas', 'perturbed'), default='replicas',
+                    help='N > 1: every GPU runs the nominal tree (default) or member `rank` of the perturbed ensemble')
     ap.add_argument('--c5-members', type=int, default=C5_MEMBERS)
     ap.add_argument('--c5-steps', type=int, default=C5_CYCLES * C5_NT)
     args = ap.parse_args()
@@ -437,7 +450,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.resume()                        # from before the warm-up on: short timed regions still get samples
-    p = tree_member(args.order, args.Nx, args.Nt, rank, theta=args.theta)
+    p = tree_member(args.order, args.Nx, args.Nt, member_of(args, rank), theta=args.theta)
     # the library enqueues on a torch stream, so torch CUDA events time exactly its kernels
     stream = torch.cuda.Stream(device=local_rank)
     an = af.ArteryNetwork(p, device=local_rank, stream=stream.cuda_stream)
