@@ -2553,28 +2553,34 @@ static int join_subs(af_net* n) {
 }
 
 // One persistent kernel pair per device at a time (per process): two pairs at once could each hold part of the
-// SMs and wait for CTAs that never become resident.  af_net_step takes the lease for the work it enqueues and a
-// host function at the end of that work gives it back; a call that finds the lease taken simply uses the
-// per-step launches (same results), e.g. two networks stepped concurrently from two threads.
-// (Calls on the handle that already holds it share the lease: back-to-back af_net_step calls stay persistent.)
+// SMs and wait for CTAs that never become resident.  af_net_step takes the lease for the work it enqueues and
+// marks the end of that work with an event; a call from ANOTHER handle that finds the event not yet reached
+// simply uses the per-step launches (same results), e.g. two networks stepped concurrently from two threads.
+// (An event, not a host function at the end of the work: cudaLaunchHostFunc costs ~0.25 ms of stream time.)
 struct PersistLease {
   std::mutex mu;
-  const af_net* owner = nullptr;
-  int count = 0;
+  const af_net* owner = nullptr;     // only ever compared
+  cudaEvent_t done = nullptr;        // end of the owner's enqueued persistent work
   bool acquire(const af_net* n) {
     std::lock_guard<std::mutex> lk(mu);
-    if (count > 0 && owner != n) return false;
+    if (!done && cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      done = nullptr;
+      return false;
+    }
+    if (owner && owner != n) {
+      if (cudaEventQuery(done) != cudaSuccess) { cudaGetLastError(); return false; }
+      owner = nullptr;
+    }
     owner = n;
-    ++count;
     return true;
   }
-  void release() {
+  void mark_end(cudaStream_t s) {
     std::lock_guard<std::mutex> lk(mu);
-    if (count > 0 && --count == 0) owner = nullptr;
+    if (cudaEventRecord(done, s) != cudaSuccess) cudaGetLastError();
   }
 };
 static PersistLease g_persist_lease[64];
-static void CUDART_CB persist_release(void* p) { static_cast<PersistLease*>(p)->release(); }
 
 extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
   int rc = check(n);
@@ -2596,10 +2602,10 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
       g_persist_lease[n->device].acquire(n))
     lease = &g_persist_lease[n->device];
   if (lease) {
-    // given back when the stream has run everything enqueued below (also on an error return)
+    // the lease ends where the stream has run everything enqueued below (also on an error return)
     struct Release {
       PersistLease* l; cudaStream_t s;
-      ~Release() { if (cudaLaunchHostFunc(s, persist_release, l) != cudaSuccess) { cudaGetLastError(); l->release(); } }
+      ~Release() { l->mark_end(s); }
     } release{lease, n->stream};
     // chunks of up to kChunk steps; a chunk ends before a step whose Un is dumped (an:920-938: Un of t_n is
     // stored BEFORE the solve of step n), so snapshots stay ordinary stream-ordered work between two chunks
