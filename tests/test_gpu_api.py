@@ -502,3 +502,18 @@ def test_cache_can_be_disabled(tmp_path):
     env = dict(os.environ, AF_CACHE_MB='0')
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_schedule_follows_the_shape_of_the_network():
+    """af_net_schedule: a multi-warp single network runs the persistent kernel pair, a one-warp network
+    (41 vertices) and an ensemble the per-step launches with grid-wide waits."""
+    import bloodflow_b200.arteryfe as af
+    from bloodflow_b200 import _ffi
+    from bloodflow_b200 import ensemble as en
+    from bloodflow_b200.synthetic import tree_param
+    tree = af.ArteryNetwork(tree_param(4, Nx=400, Nt=2000))
+    assert tree._dev.schedule() == _ffi.AF_SCHEDULE_PERSISTENT
+    small = af.ArteryNetwork(af.ParamParser(os.path.join(GOLDEN, 'golden_c1.cfg')))
+    assert small._dev.schedule() == _ffi.AF_SCHEDULE_PER_STEP
+    ens = en.EnsembleNetwork(tree_param(4, Nx=100, Nt=2000), 8)
+    assert ens.dev.schedule() == _ffi.AF_SCHEDULE_PER_STEP
