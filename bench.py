@@ -261,12 +261,12 @@ def phase_shares(dev, stream, g0, n, Nt, torch):
 def launches_in(dev_schedule, W, K, Nt, mask, chunk=64):
     """Kernels the library enqueues for af_net_step(W, K) on a single network: the per-step schedules launch the
     boundary and the artery kernel every step; the persistent schedule one pair per chunk (chunks end at multiples
-    of `chunk` steps and before a step whose Un is dumped); plus one dump kernel per snapshot and the four
+    of `chunk` steps and before a step whose Un is dumped); plus one dump kernel per snapshot and the three
     kernels that re-base the flags / empty the mailbox at the start of the call."""
     due = np.tile(mask, 2 + (W + K) // Nt)[W:W + K] != 0
     n_dumps = int(due.sum())
     if dev_schedule != 2:
-        return 2 * K + n_dumps + (4 if dev_schedule == 1 else 0), n_dumps, K
+        return 2 * K + n_dumps + (3 if dev_schedule == 1 else 0), n_dumps, K
     chunks, g = 0, W
     while g < W + K:
         n = 1
@@ -274,7 +274,7 @@ def launches_in(dev_schedule, W, K, Nt, mask, chunk=64):
             n += 1
         chunks += 1
         g += n
-    return 2 * chunks + n_dumps + 4, n_dumps, chunks
+    return 2 * chunks + n_dumps + 3, n_dumps, chunks
 
 
 def end_to_end(args, rank, local_rank, K):

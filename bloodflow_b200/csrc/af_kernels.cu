@@ -167,10 +167,11 @@ struct NetDev {
   int stop_on_fail;            // single networks: every later launch returns at once (DOLFIN raises, ar:244)
   // Dataflow between the kernels of the time loop (single networks, T >= 64): instead of waiting for the
   // whole previous grid, a task waits for exactly the arteries / junctions it depends on.
-  //   f_art[ba] = number of time steps artery ba has completed (g + 1 after step g)
-  //   f_in[ba], f_out[ba] = g + 1 once the Dirichlet data of the inlet / outlet end for step g is written
+  //   f_art[ba] = number of time steps artery ba has completed (g + 1 after step g): junction / leaf tasks wait for it
+  //   f_out[ba] = g + 1 once the junction whose PARENT vessel is ba has finished step g (its warm start x is
+  //               complete for its next instance; per-step launches only)
+  //   The Dirichlet data travels the other way through the mailbox below.
   unsigned* f_art;
-  unsigned* f_in;
   unsigned* f_out;
   double* mbox;                   // [2][nb*na*4] Dirichlet mailbox, slot set = parity of the time step
   const int* art_perm;            // persistent artery kernel: artery of CTA blockIdx.x (nullptr: identity)
@@ -1315,8 +1316,6 @@ k_artery_p(NetDev nd, int cur, long long g0, int n_steps, int log_slot0, int n_l
   int prev_its = nd.art_its[ba];
   // holder values that no junction / leaf delivers keep what they were (root: A_in; leaf: q_out)
   if (tid < 4) bcv[tid] = nd.bc[ba * 4 + tid];
-  const int n_wait = nd.nj > 0 || nd.nl > 0;     // (a lone vessel without outlet model has nothing to wait for)
-  (void)n_wait;
   for (int s = 0; s < n_steps; ++s, cur ^= 1) {
     const long long g = g0 + s;
     // a failed artery solve ends the run at its step (DOLFIN raises there, ar:244)
@@ -2270,7 +2269,6 @@ extern "C" int af_net_create(const af_desc* d, af_net** out) {
   AF_TRY(n->dalloc(&nd.flags, nd.nb));
   AF_TRY(n->dalloc(&nd.fail_step, 1));
   AF_TRY(n->dalloc(&nd.f_art, nba));
-  AF_TRY(n->dalloc(&nd.f_in, nba));
   AF_TRY(n->dalloc(&nd.f_out, nba));
   AF_TRY(n->dalloc(&nd.mbox, nd.nb == 1 ? 2 * nba * 4 : 1));
   AF_TRY(n->dalloc(&n->scratch, 4096));
@@ -2592,7 +2590,6 @@ extern "C" int af_net_step(af_net* n, int64_t n_first, int64_t n_steps) {
     // the flags count time steps: everything up to step n_first - 1 is complete, nothing of step n_first is
     const int nba = n->nd.nb * n->nd.na;
     k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_art, nba, (unsigned)n_first);
-    k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_in, nba, (unsigned)n_first);
     k_set_flags<<<(nba + 127) / 128, 128, 0, n->stream>>>(n->nd.f_out, nba, (unsigned)n_first);
     k_fill_u64<<<(8 * nba + 127) / 128, 128, 0, n->stream>>>((unsigned long long*)n->nd.mbox, 8 * nba, AF_MBOX_EMPTY);
     AF_CUDA(cudaGetLastError());
