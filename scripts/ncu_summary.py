@@ -18,7 +18,8 @@ KEEP = (
     'sm__cycles_elapsed.max', 'smsp__cycles_active.avg', 'launch__grid_size', 'launch__block_size',
     'launch__shared_mem_per_block_dynamic',
     # L2 and DRAM throughput (north_star: "achieved HBM and L2 GB/s")
-    'lts__t_bytes.sum', 'lts__t_bytes.sum.per_second', 'lts__t_sector_hit_rate.pct',
+    'lts__t_bytes.sum', 'lts__t_bytes.sum.per_second', 'lts__t_sectors.sum', 'lts__t_sectors.sum.per_second',
+    'lts__t_sector_hit_rate.pct',
     'lts__t_sectors.avg.pct_of_peak_sustained_elapsed', 'dram__bytes.sum.per_second',
     'dram__throughput.avg.pct_of_peak_sustained_elapsed',
     # executed FP64 work
@@ -45,6 +46,16 @@ def main(path, vertices=0):
                     stalls.append((float(r[k]), name[len(STALL):-len('_per_issue_active.ratio')]))
                 except ValueError:
                     pass
+        try:
+            # achieved L2 throughput: 32-byte sectors per second (the report's unit prefix is in the units row)
+            k = col['lts__t_sectors.sum.per_second']
+            val, unit = float(r[k].replace(',', '')), units[k]
+            scale = {'sector/s': 1.0, 'Ksector/s': 1e3, 'Msector/s': 1e6, 'Gsector/s': 1e9, 'Tsector/s': 1e12,
+                     'sector/ns': 1e9, 'sector/us': 1e6, 'sector/ms': 1e3}.get(unit)
+            if scale:
+                print('   achieved L2 throughput (lts__t_sectors.sum.per_second x 32 B): %.1f GB/s' % (val * scale * 32 / 1e9))
+        except (KeyError, ValueError):
+            pass
         if vertices:
             try:
                 g = lambda m: float(r[col['smsp__sass_thread_inst_executed_op_%s_pred_on.sum' % m]].replace(',', ''))   # noqa: E731
