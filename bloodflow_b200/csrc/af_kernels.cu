@@ -737,8 +737,10 @@ __device__ __forceinline__ CellInt artery_cell(const ArteryCtx& c, const CellCoe
 template <int T>
 __device__ __forceinline__ void cells_to_smem(const ArteryCtx& c, const CellCoef& ccu, const double* tab, int S,
                                               const double* sA, const double* sq, double* pa, double* pb,
-                                              double* pc, double* lo) {
-  const int tid = threadIdx.x, i0 = 4 * tid;
+                                              double* pc, double* lo, int tid = threadIdx.x) {
+  // (`tid`: the thread whose four cells are integrated -- normally the caller itself; the cell integrals depend
+  // on the iterate in shared memory only, so any thread can stand in for another, see artery_newton)
+  const int i0 = 4 * tid;
   if (T == 32) {
     // one-warp (ensemble) kernel: ONE copy of the cell routine, executed four times.
     // With 16 independent one-warp CTAs per SM the instruction cache, not ILP, is
@@ -891,7 +893,7 @@ template <int T, class Hook>
 __device__ __forceinline__ int artery_newton(const NetDev& nd, ArteryCtx& c, const CellCoef& ccu, const double* tab,
                                              int S, double* sA, double* sq, double* Lo, double* pa, double* pb,
                                              double* pc, double* red, int expect, uint32_t& fl, Hook&& dirichlet_hook,
-                                             long long tl_g, int a) {
+                                             long long tl_g, int a, bool wk_split = false) {
   const int tid = threadIdx.x;
   double EA[4], Eq[4];          // explicit part of the residual of the own vertices
   int it = 0;
@@ -908,7 +910,17 @@ __device__ __forceinline__ int artery_newton(const NetDev& nd, ArteryCtx& c, con
     const bool first = (it == 0);
     // ---- full pass: cells -> shared memory, then rows (residual + Jacobian) and level 0 of the reduction
     Row rb, rd;
-    cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
+    if (T > 32 && first && wk_split) {
+      // Leaf artery of the persistent kernel: its second warp has just run the Windkessel of this step (set_bcs,
+      // an:780-786) while the others integrated their cells; the first warp, which would only wait now,
+      // integrates the second warp's cells as well.  Same arithmetic on the same inputs, another thread.
+      const int w = tid >> 5;
+#pragma unroll 1
+      for (int rep = 0; rep < (w == 0 ? 2 : (w == 1 ? 0 : 1)); ++rep)
+        cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo, tid + 32 * rep);
+    } else {
+      cells_to_smem<T>(c, ccu, tab, S, sA, sq, pa, pb, pc, Lo);
+    }
     if (first) dirichlet_hook();
     cta_sync<T>();
     double part = rows_from_smem<T>(c, sA, sq, pa, pb, pc, Lo, first, EA, Eq, rb, rd);
@@ -1367,7 +1379,7 @@ k_artery_p(NetDev nd, int cur, long long g0, int n_steps, int log_slot0, int n_l
         c.gqin = qin_s;
         if (tid == 0) nd.bc[ba * 4 + 1] = c.gqin;      // arteries[0].q_in = q_in (an:777): the holder keeps it
       }
-    }, g, a);
+    }, g, a, c.leaf);
     if (tid == 0) AF_TL(nd, g, a, 6);
     // update_solution (ar:247-251): Un <- U, into the other buffer
     {
