@@ -2089,6 +2089,9 @@ static cudaError_t prepare_artery(af_net* n) {
     // a vessel the artery kernel knows as one, and all CTAs of both kernels must fit the device together
     n->persist = e == cudaSuccess && n->pdl && persistent_fits<(T >= 64 ? T : 64)>(n);
     if (const char* env = getenv("AF_NO_PERSIST")) if (atoi(env)) n->persist = false;
+    // Kernel profilers (Nsight Compute) run one kernel at a time: the persistent pair, whose kernels wait for each
+    // other, would only end on its time-outs.  Under a profiler the per-step launches are used (same device code).
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH")) n->persist = false;
     if (n->persist) {
       // CTAs are handed to the SMs round-robin: with na CTAs on nsm SMs (nsm < na <= 2 nsm) the CTAs
       // na - nsm .. nsm - 1 keep an SM to themselves.  Those go to the upper generations of the tree (arteries are
